@@ -151,7 +151,7 @@ def test_triangulation_zero_flow_returns_mesh_surface():
     # NB quirk C3: sampleImage at integer coordinates returns the lower-right neighbour's depth, so the
     # measured point is not exactly the prediction; on a smooth surface the point stays on the mesh.
     err = np.abs(got[:, :3] / got[:, 3:4] - X[:, :3] / X[:, 3:4]).max(1)
-    assert np.median(err) < 1e-3 * sc.scale and err.max() < 0.05 * sc.scale
+    assert np.median(err) < 5e-3 * sc.scale and err.max() < 0.05 * sc.scale
     # rows come out in row-major order with 7 columns, normals scaled by pdf
     tri = triangulate_pixels([flow], sc.cameras[1], [sc.cameras[2]], depth)
     assert tri.shape == (int(valid.sum()), 7)
