@@ -1,0 +1,127 @@
+/*
+ * meshrecon_b200.h -- C ABI of the B200-native dense-correspondence hot path of
+ * addam/mesh-reconstruction (libmeshrecon_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces one C++ interface of the
+ * reference (cited as file:line into the upstream tree).  Signatures are OpenCV-free:
+ * plain pointers and sizes.  The cv::Mat shim a maintainer adds on the reference side
+ * is shown in INTEGRATION.md; the in-repo C++ mirror of recon.hpp lives in
+ * mesh_reconstruction_b200/csrc/recon_b200.hpp.
+ *
+ * Conventions (same as the reference, recon.hpp / SURVEY.md 8b):
+ *   - images are row-major, top-down, densely packed (stride == width * channels);
+ *   - camera matrices are 4x4 float32 row-major, acting on column vectors, rows giving
+ *     clip x, y, z, w (io_export_tracks.py:22-28,59-66);
+ *   - depth maps hold NDC z, background == 1.0f exactly (recon.hpp:30);
+ *   - a flow record is 4 floats (u, v, variance, 0) per pixel (flow.cpp:37-40);
+ *   - a point row is 7 floats (x, y, z, w, nx, ny, nz) (recon.cpp:152-155).
+ *
+ * Every buffer argument may be a HOST pointer (pageable or pinned) or a DEVICE pointer
+ * of the context's GPU; the library detects which (cudaPointerGetAttributes) and stages
+ * host buffers through the context's stream.  Calls on one context are serialised by the
+ * caller (the reference is single-threaded); different contexts are independent.
+ *
+ * Error convention: every function returns MR_OK (0) or a negative MR_E* code and never
+ * calls exit(); mr_last_error() returns a human readable message.  There is NO CPU
+ * fallback: without a usable CUDA device mr_create() fails with MR_ENODEVICE.
+ */
+#ifndef MESHRECON_B200_H
+#define MESHRECON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_OK 0
+#define MR_EINVAL (-1)    /* bad argument (null pointer, size mismatch, S out of range) */
+#define MR_ENODEVICE (-2) /* no CUDA device / device index out of range */
+#define MR_ECUDA (-3)     /* a CUDA runtime call or kernel failed; see mr_last_error */
+#define MR_ENOMESH (-4)   /* a render call before mr_load_mesh */
+#define MR_ENOMEM (-5)    /* device allocation failed */
+
+#define MR_MAX_SIDE 16              /* max side cameras per main camera */
+#define MR_BACKGROUND_DEPTH 1.0f    /* recon.hpp:30 */
+
+typedef struct mr_context mr_context;
+
+/* ---- lifetime ------------------------------------------------------------------
+ * Replaces spawnRender(hint) / RenderGLX::RenderGLX (render_glx.cpp:57-62,152-208):
+ * the render size is fixed per context (heuristic.cpp:548-551). */
+int mr_create(mr_context **ctx, int device, int width, int height);
+void mr_destroy(mr_context *ctx);                    /* RenderGLX::~RenderGLX render_glx.cpp:210-227 */
+const char *mr_last_error(const mr_context *ctx);    /* ctx may be NULL: last creation error */
+int mr_version(void);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+void *mr_stream(mr_context *ctx);
+/* Block until all enqueued work of the context finished. */
+int mr_synchronize(mr_context *ctx);
+
+/* ---- Render (recon.hpp:93-99) --------------------------------------------------- */
+/* Render::loadMesh  render_glx.cpp:230-258.  vertices: V x 4 homogeneous float32,
+ * faces: F x 3 int32 vertex indices. */
+int mr_load_mesh(mr_context *ctx, const float *vertices_xyzw, int n_vertices, const int32_t *faces, int n_faces);
+/* Render::depth  render_glx.cpp:369-397.  out: H*W float32 NDC z. */
+int mr_depth(mr_context *ctx, const float camera[16], float *out_depth);
+/* Render::projected  render_glx.cpp:261-367 + shader.vert:9-13 + shader.frag:11-25.
+ * frame: H*W uint8 (side camera's gray frame); out_rgb: H*W*3 uint8 (R = predicted gray,
+ * G = B = 255 where visible and in-frame, else 0,0,0). */
+int mr_projected(mr_context *ctx, const float camera[16], const uint8_t *frame, const float projector[16],
+                 uint8_t *out_rgb);
+
+/* ---- util.cpp / flow.cpp free functions (recon.hpp:40-55) ----------------------- */
+/* mixBackground  util.cpp:366-387.  depth is IN/OUT (masked pixels are set to 1.0f). */
+int mr_mix_background(mr_context *ctx, const uint8_t *image_rgb, const uint8_t *background, float *depth_inout,
+                      uint8_t *out_mixed);
+/* calculateFlow  flow.cpp:19-42.  out: H*W*4 float32 (u, v, variance, 0).
+ * use_farneback != 0 selects the reference's -f branch, which is NOT implemented in this
+ * round: the call then fails with MR_EINVAL, it never falls back. */
+int mr_calculate_flow(mr_context *ctx, const uint8_t *prev, const uint8_t *next, int use_farneback, float *out_flow4);
+/* flowRemap  util.cpp:390-403.  flow: H*W*stride_floats float32 with (u, v) first
+ * (stride_floats = 2 for CV_32FC2 or 4 for the flow record); out: H*W uint8. */
+int mr_flow_remap(mr_context *ctx, const float *flow, int stride_floats, const uint8_t *image, uint8_t *out);
+/* compare  util.cpp:332-361.  out: H*W float32. */
+int mr_compare(mr_context *ctx, const uint8_t *prev, const uint8_t *next, float *out);
+/* imageGradient  util.cpp:465-479 (single-channel float input). out: H*W*2 float32. */
+int mr_image_gradient(mr_context *ctx, const float *image, float *out_grad2);
+/* triangulatePixels  util.cpp:167-329.  flows: n_side pointers to H*W*4 float32;
+ * cameras: n_side*16 float32; out_points: capacity H*W*7 float32; *out_count = M rows,
+ * in row-major pixel order. */
+int mr_triangulate_pixels(mr_context *ctx, const float *const *flows, int n_side, const float main_camera[16],
+                          const float *cameras, const float *depth, float *out_points, int *out_count);
+/* extractCameraCenter  util.cpp:33-41 (host-side helper, dehomogenised). */
+int mr_extract_camera_center(const float camera[16], float out_center3[3]);
+
+/* ---- fused, device-resident main-frame step (recon.cpp:65-119) ------------------
+ * One iteration of the reference's outer loop for main camera `main_camera`:
+ *   depth = render->depth(main)                                   recon.cpp:70
+ *   for each side i: projected -> mixBackground -> calculateFlow   recon.cpp:85-89
+ *   triangulatePixels(flows, main, sides, depth)                   recon.cpp:114
+ * without materialising intermediates on the host.  Results are identical to calling
+ * the individual entry points in that order.  out_points (capacity H*W*7 floats, host or
+ * device) may be NULL to keep the rows in the context (mr_points_device). */
+int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                          const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
+                          int *out_count);
+/* Device pointer to the point rows produced by the last mr_process_main_frame /
+ * mr_triangulate_pixels (valid until the next call), and their count. */
+const float *mr_points_device(mr_context *ctx, int *out_count);
+/* Intermediates of the last mr_process_main_frame (device pointers, valid until the next
+ * call): the final (mixed) depth, and the flow record of side camera i. For tests. */
+const float *mr_last_depth_device(mr_context *ctx);
+const float *mr_last_flow_device(mr_context *ctx, int side);
+const uint8_t *mr_last_mixed_device(mr_context *ctx, int side);
+
+/* Debug / benchmarking knob (process-wide): 0 = plane-per-stage variational-refinement
+ * kernels, 1 = fused shared-memory tile kernel (default).  Both produce identical bits. */
+int mr_set_vr_impl(int impl);
+
+/* Number of kernels this library launched on the context since creation (bench.py's
+ * gpu_launches claim). */
+uint64_t mr_launch_count(const mr_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHRECON_B200_H */

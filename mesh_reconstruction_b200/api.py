@@ -1,0 +1,308 @@
+"""ctypes binding of ``libmeshrecon_b200.so`` mirroring the reference's C++ interface
+(``recon.hpp``).  Every function takes NumPy arrays (host buffers) or torch CUDA tensors
+(device buffers, zero-copy) and forwards raw pointers to the C ABI.
+
+Reference interface -> here:
+  spawnRender(hint)                     recon.hpp:100     -> spawnRender(width, height, device)
+  Render::loadMesh/depth/projected      recon.hpp:93-99   -> Render.loadMesh/depth/projected
+  calculateFlow(prev, next, farneback)  recon.hpp:40      -> calculateFlow
+  mixBackground(image, bg, Mat &depth)  recon.hpp:49      -> mixBackground (depth mutated in place)
+  triangulatePixels(flows, P, cams, d)  recon.hpp:44      -> triangulatePixels
+  compare / flowRemap / imageGradient   recon.hpp:45,50,55
+  extractCameraCenter                   recon.hpp:43
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MR_MAX_SIDE = 16
+_ERRNAMES = {-1: "MR_EINVAL", -2: "MR_ENODEVICE", -3: "MR_ECUDA", -4: "MR_ENOMESH", -5: "MR_ENOMEM"}
+
+
+class MeshReconError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libmeshrecon_b200.so")
+
+
+def load_library():
+    """Loads the CUDA library; raises (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MeshReconError(-2, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 "(there is no CPU fallback for the hot path)")
+    L = C.CDLL(path)
+    vp, ip, fpp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)
+    L.mr_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+    L.mr_destroy.argtypes = [vp]
+    L.mr_destroy.restype = None
+    L.mr_last_error.argtypes = [vp]
+    L.mr_last_error.restype = C.c_char_p
+    L.mr_version.restype = C.c_int
+    L.mr_stream.argtypes = [vp]
+    L.mr_stream.restype = vp
+    L.mr_synchronize.argtypes = [vp]
+    L.mr_load_mesh.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.mr_depth.argtypes = [vp, vp, vp]
+    L.mr_projected.argtypes = [vp, vp, vp, vp, vp]
+    L.mr_mix_background.argtypes = [vp, vp, vp, vp, vp]
+    L.mr_calculate_flow.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.mr_flow_remap.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.mr_compare.argtypes = [vp, vp, vp, vp]
+    L.mr_image_gradient.argtypes = [vp, vp, vp]
+    L.mr_triangulate_pixels.argtypes = [vp, fpp, C.c_int, vp, vp, vp, vp, ip]
+    L.mr_extract_camera_center.argtypes = [vp, vp]
+    L.mr_process_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
+    L.mr_points_device.argtypes = [vp, ip]
+    L.mr_points_device.restype = vp
+    L.mr_last_depth_device.argtypes = [vp]
+    L.mr_last_depth_device.restype = vp
+    L.mr_last_flow_device.argtypes = [vp, C.c_int]
+    L.mr_last_flow_device.restype = vp
+    L.mr_last_mixed_device.argtypes = [vp, C.c_int]
+    L.mr_last_mixed_device.restype = vp
+    L.mr_launch_count.argtypes = [vp]
+    L.mr_launch_count.restype = C.c_uint64
+    L.mr_set_vr_impl.argtypes = [C.c_int]
+    _LIB = L
+    return L
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, dtype=None, shape=None, name="argument"):
+    """Raw pointer of a C-contiguous NumPy array or torch tensor (plus a keep-alive ref)."""
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError(f"{name}: tensor must be contiguous")
+        return x.data_ptr(), x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+    return a.ctypes.data, a
+
+
+def _mat16(m):
+    a = np.ascontiguousarray(np.asarray(m, np.float32).reshape(16))
+    return a.ctypes.data, a
+
+
+class Context:
+    """Owns one ``mr_context`` (one per GPU and render size)."""
+
+    def __init__(self, width, height, device=0):
+        self.lib = load_library()
+        self.W, self.H, self.device = int(width), int(height), int(device)
+        h = C.c_void_p()
+        rc = self.lib.mr_create(C.byref(h), self.device, self.W, self.H)
+        if rc:
+            raise MeshReconError(rc, self.lib.mr_last_error(None).decode())
+        self.h = h
+
+    def check(self, rc):
+        if rc:
+            raise MeshReconError(rc, self.lib.mr_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(self.lib.mr_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.mr_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.mr_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_CTX = {}
+
+
+def _ctx(width, height, device=0):
+    key = (int(width), int(height), int(device))
+    if key not in _CTX:
+        _CTX[key] = Context(*key)
+    return _CTX[key]
+
+
+class Render:
+    """``class Render`` (recon.hpp:93-99) backed by the CUDA rasteriser."""
+
+    def __init__(self, width, height, device=0, ctx=None):
+        self.ctx = ctx or _ctx(width, height, device)
+        self.W, self.H = self.ctx.W, self.ctx.H
+
+    def loadMesh(self, vertices, faces=None):
+        if faces is None:  # accept a (vertices, faces) Mesh tuple like the reference's struct
+            vertices, faces = vertices
+        pv, kv = _ptr(vertices, np.float32, name="vertices")
+        pf, kf = _ptr(faces, np.int32, name="faces")
+        nv = int(kv.shape[0])
+        nf = int(kf.shape[0])
+        self.ctx.check(self.ctx.lib.mr_load_mesh(self.ctx.h, pv, nv, pf, nf))
+
+    def depth(self, camera, out=None):
+        pc, kc = _mat16(camera)
+        if out is None:
+            out = np.empty((self.H, self.W), np.float32)
+        po, _ = _ptr(out, np.float32)
+        self.ctx.check(self.ctx.lib.mr_depth(self.ctx.h, pc, po))
+        return out
+
+    def projected(self, camera, frame, projector, out=None):
+        pc, kc = _mat16(camera)
+        pp, kp = _mat16(projector)
+        pf, kf = _ptr(frame, np.uint8, (self.H, self.W) if not _is_torch(frame) else None, "frame")
+        if out is None:
+            out = np.empty((self.H, self.W, 3), np.uint8)
+        po, _ = _ptr(out, np.uint8)
+        self.ctx.check(self.ctx.lib.mr_projected(self.ctx.h, pc, pf, pp, po))
+        return out
+
+
+def spawnRender(width, height, device=0):
+    """``spawnRender(hint)`` (recon.hpp:100): the render size is the clip size
+    (heuristic.cpp:548-551)."""
+    return Render(width, height, device)
+
+
+def _hw(x):
+    return int(x.shape[0]), int(x.shape[1])
+
+
+def mixBackground(image, background, depth, device=0):
+    """util.cpp:366-387.  ``depth`` (float32 H x W, NumPy or CUDA tensor) is modified in place."""
+    H, W = _hw(background)
+    ctx = _ctx(W, H, device)
+    if not _is_torch(depth):
+        assert depth.dtype == np.float32 and depth.flags.c_contiguous, "depth must be a contiguous float32 array (in/out)"
+    pi, ki = _ptr(image, np.uint8)
+    pb, kb = _ptr(background, np.uint8)
+    pd, kd = _ptr(depth, np.float32)
+    out = np.empty((H, W), np.uint8)
+    ctx.check(ctx.lib.mr_mix_background(ctx.h, pi, pb, pd, out.ctypes.data))
+    return out
+
+
+def calculateFlow(prev, next, useFarneback=False, device=0, out=None):
+    """flow.cpp:19-42 -> H x W x 4 float32 ``(u, v, variance, 0)``."""
+    H, W = _hw(prev)
+    ctx = _ctx(W, H, device)
+    pp, kp = _ptr(prev, np.uint8)
+    pn, kn = _ptr(next, np.uint8)
+    if out is None:
+        out = np.empty((H, W, 4), np.float32)
+    po, _ = _ptr(out, np.float32)
+    ctx.check(ctx.lib.mr_calculate_flow(ctx.h, pp, pn, int(bool(useFarneback)), po))
+    return out
+
+
+def flowRemap(flow, image, device=0):
+    """util.cpp:390-403."""
+    H, W = _hw(image)
+    ctx = _ctx(W, H, device)
+    stride = int(flow.shape[2])
+    pf, kf = _ptr(flow, np.float32)
+    pi, ki = _ptr(image, np.uint8)
+    out = np.empty((H, W), np.uint8)
+    ctx.check(ctx.lib.mr_flow_remap(ctx.h, pf, stride, pi, out.ctypes.data))
+    return out
+
+
+def compare(prev, next, device=0):
+    """util.cpp:332-361."""
+    H, W = _hw(prev)
+    ctx = _ctx(W, H, device)
+    pp, kp = _ptr(prev, np.uint8)
+    pn, kn = _ptr(next, np.uint8)
+    out = np.empty((H, W), np.float32)
+    ctx.check(ctx.lib.mr_compare(ctx.h, pp, pn, out.ctypes.data))
+    return out
+
+
+def imageGradient(image, device=0):
+    """util.cpp:465-479 (single-channel float32 input)."""
+    H, W = _hw(image)
+    ctx = _ctx(W, H, device)
+    pi, ki = _ptr(image, np.float32)
+    out = np.empty((H, W, 2), np.float32)
+    ctx.check(ctx.lib.mr_image_gradient(ctx.h, pi, out.ctypes.data))
+    return out
+
+
+def extractCameraCenter(camera):
+    """util.cpp:33-41 (returned dehomogenised, 3 floats)."""
+    lib = load_library()
+    pc, kc = _mat16(camera)
+    out = np.empty(3, np.float32)
+    rc = lib.mr_extract_camera_center(pc, out.ctypes.data)
+    if rc:
+        raise MeshReconError(rc, "mr_extract_camera_center")
+    return out
+
+
+def triangulatePixels(flows, mainCamera, cameras, depth, device=0):
+    """util.cpp:167-329 -> M x 7 float32 rows ``(x, y, z, w, nx, ny, nz)`` in row-major pixel order."""
+    H, W = _hw(depth)
+    ctx = _ctx(W, H, device)
+    S = len(flows)
+    if not (1 <= S <= MR_MAX_SIDE) or len(cameras) != S:
+        raise MeshReconError(-1, "flows and cameras must have the same length in 1..16")
+    keep = [_ptr(f, np.float32) for f in flows]
+    arr = (C.c_void_p * S)(*[k[0] for k in keep])
+    pm, km = _mat16(mainCamera)
+    cams = np.ascontiguousarray(np.stack([np.asarray(c, np.float32).reshape(16) for c in cameras]))
+    pd, kd = _ptr(depth, np.float32)
+    out = np.empty((H * W, 7), np.float32)
+    m = C.c_int(0)
+    ctx.check(ctx.lib.mr_triangulate_pixels(ctx.h, arr, S, pm, cams.ctypes.data, pd, out.ctypes.data, C.byref(m)))
+    return out[:m.value].copy()
+
+
+def process_main_frame(render, main_frame, main_camera, side_frames, side_cameras, out=None, want_host=True):
+    """One iteration of the reference's outer loop (recon.cpp:65-119), fused and
+    device-resident.  Returns the M x 7 rows (NumPy) or, with ``want_host=False``, just M
+    (rows stay on the device: ``Context.lib.mr_points_device``)."""
+    ctx = render.ctx
+    S = len(side_frames)
+    keep = [_ptr(f, np.uint8) for f in side_frames]
+    arr = (C.c_void_p * S)(*[k[0] for k in keep])
+    pf, kf = _ptr(main_frame, np.uint8)
+    pm, km = _mat16(main_camera)
+    cams = np.ascontiguousarray(np.stack([np.asarray(c, np.float32).reshape(16) for c in side_cameras]))
+    m = C.c_int(0)
+    if out is not None:
+        po, ko = _ptr(out, np.float32)
+    elif want_host:
+        out = np.empty((ctx.H * ctx.W, 7), np.float32)
+        po = out.ctypes.data
+    else:
+        po = None
+    ctx.check(ctx.lib.mr_process_main_frame(ctx.h, pf, pm, S, arr, cams.ctypes.data, po, C.byref(m)))
+    if want_host and not _is_torch(out):
+        return out[:m.value]
+    return m.value

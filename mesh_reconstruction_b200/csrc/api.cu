@@ -1,0 +1,445 @@
+// api.cu -- extern "C" entry points of libmeshrecon_b200.so (include/meshrecon_b200.h).
+// Host-side plumbing only: argument checks, host<->device staging, stage sequencing.
+// There is no CPU implementation of any stage behind these calls.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+thread_local std::string g_mr_create_error;
+int g_mr_vr_impl = 0;
+
+int mr_fail(mr_context *ctx, int code, const char *what, const char *detail)
+{
+    std::string msg = std::string(what ? what : "") + ": " + (detail ? detail : "");
+    if (ctx) ctx->err = msg;
+    else g_mr_create_error = msg;
+    return code;
+}
+
+void *mr_buf_raw(mr_context *ctx, const char *name, size_t bytes)
+{
+    DevBuf &b = ctx->bufs[name];
+    if (b.p && bytes <= b.bytes) return b.p;
+    if (bytes == 0) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t alloc = (bytes + 255) & ~(size_t)255;
+    if (cudaMalloc(&b.p, alloc) != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.bytes = alloc;
+    return b.p;
+}
+
+bool mr_is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+const void *mr_in(mr_context *ctx, const void *p, size_t bytes, const char *staging)
+{
+    if (mr_is_device_ptr(p)) return p;
+    void *d = mr_buf_raw(ctx, staging, bytes);
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+    return d;
+}
+
+int mr_out(mr_context *ctx, void *dst, const void *src_dev, size_t bytes)
+{
+    if (dst == src_dev) return MR_OK;
+    MR_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    return MR_OK;
+}
+
+static Mat4 to_mat4(const float *m)
+{
+    Mat4 r;
+    memcpy(r.m, m, sizeof(r.m));
+    return r;
+}
+
+#define CHECK_CTX(ctx) \
+    if (!(ctx)) return MR_EINVAL
+#define CHECK_ARG(ctx, cond, msg) \
+    if (!(cond)) return mr_fail(ctx, MR_EINVAL, __func__, msg)
+#define SET_DEVICE(ctx) MR_CUDA(ctx, cudaSetDevice((ctx)->device))
+#define RC(x)                 \
+    do {                      \
+        int rc__ = (x);       \
+        if (rc__) return rc__; \
+    } while (0)
+
+extern "C" {
+
+int mr_version(void) { return 100; }
+
+int mr_create(mr_context **out, int device, int width, int height)
+{
+    if (!out) return MR_EINVAL;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || (size_t)width * height > ((size_t)1 << 30)) return mr_fail(nullptr, MR_EINVAL, "mr_create", "bad size");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return mr_fail(nullptr, MR_ENODEVICE, "mr_create", "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return mr_fail(nullptr, MR_ENODEVICE, "mr_create", "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return mr_fail(nullptr, MR_ECUDA, "mr_create", "cudaSetDevice failed");
+    if (prop.major != 10) return mr_fail(nullptr, MR_ENODEVICE, "mr_create", "device is not sm_100 (B200); kernels are built for sm_100a only");
+    mr_context *ctx = new mr_context();
+    ctx->device = device;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->N = (size_t)width * height;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_count, 64) != cudaSuccess) {
+        delete ctx;
+        return mr_fail(nullptr, MR_ECUDA, "mr_create", "stream / pinned alloc failed");
+    }
+    // pyramid geometry of compare() (util.cpp:335-351)
+    int size = width < height ? width : height, w = width, h = height, L = 0;
+    size_t off = 0;
+    for (;;) {
+        ctx->lw[L] = w; ctx->lh[L] = h; ctx->loff[L] = off;
+        off += (size_t)w * h;
+        L++;
+        if (size <= 2 || L >= MR_MAX_LEVELS) break;
+        w = (w + 1) / 2; h = (h + 1) / 2; size /= 2;
+    }
+    ctx->n_levels = L;
+    ctx->pyr_total = off;
+    int rc = mr_flow_init_tables(ctx);
+    if (rc) {
+        g_mr_create_error = ctx->err;
+        mr_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return MR_OK;
+}
+
+void mr_destroy(mr_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->bufs)
+        if (kv.second.p) cudaFree(kv.second.p);
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mr_last_error(const mr_context *ctx) { return ctx ? ctx->err.c_str() : g_mr_create_error.c_str(); }
+void *mr_stream(mr_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t mr_launch_count(const mr_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int mr_synchronize(mr_context *ctx)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+// debug / benchmarking knob: 0 = plane-per-stage VR kernels, 1 = fused tile kernel
+int mr_set_vr_impl(int impl)
+{
+    g_mr_vr_impl = impl ? 1 : 0;
+    return MR_OK;
+}
+
+int mr_load_mesh(mr_context *ctx, const float *vertices_xyzw, int n_vertices, const int32_t *faces, int n_faces)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, n_vertices >= 0 && n_faces >= 0, "negative count");
+    CHECK_ARG(ctx, n_faces == 0 || (vertices_xyzw && faces), "null mesh pointers");
+    if (n_faces == 0) return k_load_mesh(ctx, nullptr, nullptr, 0);
+    const float *dv = (const float *)mr_in(ctx, vertices_xyzw, (size_t)n_vertices * 4 * sizeof(float), "in_vtx");
+    const int32_t *df = (const int32_t *)mr_in(ctx, faces, (size_t)n_faces * 3 * sizeof(int32_t), "in_faces");
+    if (!dv || !df) return mr_fail(ctx, MR_ENOMEM, "mr_load_mesh", "staging");
+    RC(k_load_mesh(ctx, dv, df, n_faces));
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+int mr_depth(mr_context *ctx, const float camera[16], float *out_depth)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, camera && out_depth, "null argument");
+    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_depth", "loadMesh has not been called");
+    unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
+    bool dev_out = mr_is_device_ptr(out_depth);
+    float *d = dev_out ? out_depth : mr_buf<float>(ctx, "depth", ctx->N);
+    if (!vis || !d) return mr_fail(ctx, MR_ENOMEM, "mr_depth", "alloc");
+    RC(k_raster(ctx, to_mat4(camera), vis));
+    RC(k_resolve_depth(ctx, vis, d));
+    if (!dev_out) {
+        RC(mr_out(ctx, out_depth, d, ctx->N * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+// shadow pass + dilation for `projector`, leaves the dilated map in "shadow_dil"
+static int shadow_pass(mr_context *ctx, const float *projector, float **out)
+{
+    unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_side", ctx->N);
+    float *sh = mr_buf<float>(ctx, "shadow", ctx->N);
+    float *shd = mr_buf<float>(ctx, "shadow_dil", ctx->N);
+    if (!vis || !sh || !shd) return mr_fail(ctx, MR_ENOMEM, "shadow_pass", "alloc");
+    RC(k_raster(ctx, to_mat4(projector), vis));
+    RC(k_resolve_depth(ctx, vis, sh));
+    RC(k_dilate_shadow(ctx, sh, shd));
+    *out = shd;
+    return MR_OK;
+}
+
+int mr_projected(mr_context *ctx, const float camera[16], const uint8_t *frame, const float projector[16], uint8_t *out_rgb)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, camera && frame && projector && out_rgb, "null argument");
+    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_projected", "loadMesh has not been called");
+    const uint8_t *d_frame = (const uint8_t *)mr_in(ctx, frame, ctx->N, "in_side");
+    unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
+    bool dev_out = mr_is_device_ptr(out_rgb);
+    uint8_t *rgb = dev_out ? out_rgb : mr_buf<uint8_t>(ctx, "rgb", ctx->N * 3);
+    if (!d_frame || !vis || !rgb) return mr_fail(ctx, MR_ENOMEM, "mr_projected", "alloc");
+    float *shd = nullptr;
+    RC(shadow_pass(ctx, projector, &shd));
+    RC(k_raster(ctx, to_mat4(camera), vis));
+    RC(k_shade(ctx, vis, to_mat4(camera), to_mat4(projector), d_frame, shd, rgb, nullptr, nullptr, nullptr));
+    if (!dev_out) {
+        RC(mr_out(ctx, out_rgb, rgb, ctx->N * 3));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_mix_background(mr_context *ctx, const uint8_t *image_rgb, const uint8_t *background, float *depth_inout, uint8_t *out_mixed)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, image_rgb && background && depth_inout && out_mixed, "null argument");
+    const uint8_t *d_rgb = (const uint8_t *)mr_in(ctx, image_rgb, ctx->N * 3, "in_rgb");
+    const uint8_t *d_bg = (const uint8_t *)mr_in(ctx, background, ctx->N, "in_main");
+    bool dev_depth = mr_is_device_ptr(depth_inout), dev_out = mr_is_device_ptr(out_mixed);
+    float *d_depth = dev_depth ? depth_inout : (float *)mr_in(ctx, depth_inout, ctx->N * sizeof(float), "depth");
+    uint8_t *d_out = dev_out ? out_mixed : mr_buf<uint8_t>(ctx, "mixed0", ctx->N);
+    if (!d_rgb || !d_bg || !d_depth || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_mix_background", "alloc");
+    RC(k_mix_background(ctx, d_rgb, d_bg, d_depth, d_out));
+    if (!dev_depth) RC(mr_out(ctx, depth_inout, d_depth, ctx->N * sizeof(float)));
+    if (!dev_out) RC(mr_out(ctx, out_mixed, d_out, ctx->N));
+    if (!dev_depth || !dev_out) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+// device-side calculateFlow: VR -> remap -> compare -> pack (flow.cpp:29-40)
+static int calculate_flow_dev(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4)
+{
+    uint8_t *remapped = mr_buf<uint8_t>(ctx, "remapped", ctx->N);
+    if (!remapped) return mr_fail(ctx, MR_ENOMEM, "calculate_flow", "alloc");
+    RC(k_variational_refinement(ctx, d_prev, d_next, d_flow4));  // writes (u, v, 0, 0)
+    RC(k_flow_remap(ctx, d_flow4, 4, d_next, remapped));
+    RC(k_compare(ctx, d_prev, remapped, d_flow4, 4, 2));         // variance -> channel 2
+    return MR_OK;
+}
+
+int mr_calculate_flow(mr_context *ctx, const uint8_t *prev, const uint8_t *next, int use_farneback, float *out_flow4)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, prev && next && out_flow4, "null argument");
+    CHECK_ARG(ctx, !use_farneback, "Farneback branch (flow.cpp:22-26) is not implemented; no fallback is taken");
+    const uint8_t *d_prev = (const uint8_t *)mr_in(ctx, prev, ctx->N, "in_main");
+    const uint8_t *d_next = (const uint8_t *)mr_in(ctx, next, ctx->N, "in_side");
+    bool dev_out = mr_is_device_ptr(out_flow4);
+    float *d_flow = dev_out ? out_flow4 : mr_buf<float>(ctx, "flow0", ctx->N * 4);
+    if (!d_prev || !d_next || !d_flow) return mr_fail(ctx, MR_ENOMEM, "mr_calculate_flow", "alloc");
+    RC(calculate_flow_dev(ctx, d_prev, d_next, d_flow));
+    if (!dev_out) {
+        RC(mr_out(ctx, out_flow4, d_flow, ctx->N * 4 * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_flow_remap(mr_context *ctx, const float *flow, int stride_floats, const uint8_t *image, uint8_t *out)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, flow && image && out, "null argument");
+    CHECK_ARG(ctx, stride_floats >= 2 && stride_floats <= 4, "stride_floats must be 2..4");
+    const float *d_flow = (const float *)mr_in(ctx, flow, ctx->N * stride_floats * sizeof(float), "flow0");
+    const uint8_t *d_img = (const uint8_t *)mr_in(ctx, image, ctx->N, "in_side");
+    bool dev_out = mr_is_device_ptr(out);
+    uint8_t *d_out = dev_out ? out : mr_buf<uint8_t>(ctx, "remapped", ctx->N);
+    if (!d_flow || !d_img || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_flow_remap", "alloc");
+    RC(k_flow_remap(ctx, d_flow, stride_floats, d_img, d_out));
+    if (!dev_out) {
+        RC(mr_out(ctx, out, d_out, ctx->N));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_compare(mr_context *ctx, const uint8_t *prev, const uint8_t *next, float *out)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, prev && next && out, "null argument");
+    const uint8_t *d_prev = (const uint8_t *)mr_in(ctx, prev, ctx->N, "in_main");
+    const uint8_t *d_next = (const uint8_t *)mr_in(ctx, next, ctx->N, "in_side");
+    bool dev_out = mr_is_device_ptr(out);
+    float *d_out = dev_out ? out : mr_buf<float>(ctx, "variance", ctx->N);
+    if (!d_prev || !d_next || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_compare", "alloc");
+    RC(k_compare(ctx, d_prev, d_next, d_out, 1, 0));
+    if (!dev_out) {
+        RC(mr_out(ctx, out, d_out, ctx->N * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_image_gradient(mr_context *ctx, const float *image, float *out_grad2)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, image && out_grad2, "null argument");
+    const float *d_img = (const float *)mr_in(ctx, image, ctx->N * sizeof(float), "depth");
+    bool dev_out = mr_is_device_ptr(out_grad2);
+    float *d_out = dev_out ? out_grad2 : mr_buf<float>(ctx, "grad2", ctx->N * 2);
+    if (!d_img || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_image_gradient", "alloc");
+    RC(k_image_gradient(ctx, d_img, d_out));
+    if (!dev_out) {
+        RC(mr_out(ctx, out_grad2, d_out, ctx->N * 2 * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+static const char *flow_name(int i)
+{
+    static const char *names[MR_MAX_SIDE] = {"flow0", "flow1", "flow2", "flow3", "flow4", "flow5", "flow6", "flow7",
+                                              "flow8", "flow9", "flow10", "flow11", "flow12", "flow13", "flow14", "flow15"};
+    return names[i];
+}
+static const char *mixed_name(int i)
+{
+    static const char *names[MR_MAX_SIDE] = {"mixed0", "mixed1", "mixed2", "mixed3", "mixed4", "mixed5", "mixed6", "mixed7",
+                                              "mixed8", "mixed9", "mixed10", "mixed11", "mixed12", "mixed13", "mixed14", "mixed15"};
+    return names[i];
+}
+
+int mr_triangulate_pixels(mr_context *ctx, const float *const *flows, int n_side, const float main_camera[16], const float *cameras,
+                          const float *depth, float *out_points, int *out_count)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, flows && main_camera && cameras && depth && out_count, "null argument");
+    CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
+    const float *d_flows[MR_MAX_SIDE];
+    for (int i = 0; i < n_side; i++) {
+        CHECK_ARG(ctx, flows[i], "null flow pointer");
+        d_flows[i] = (const float *)mr_in(ctx, flows[i], ctx->N * 4 * sizeof(float), flow_name(i));
+        if (!d_flows[i]) return mr_fail(ctx, MR_ENOMEM, "mr_triangulate_pixels", "staging");
+    }
+    const float *d_depth = (const float *)mr_in(ctx, depth, ctx->N * sizeof(float), "depth");
+    bool dev_out = out_points && mr_is_device_ptr(out_points);
+    float *d_out = dev_out ? out_points : mr_buf<float>(ctx, "points", ctx->N * 7);
+    if (!d_depth || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_triangulate_pixels", "alloc");
+    RC(k_triangulate(ctx, d_flows, n_side, main_camera, cameras, d_depth, d_out, out_count));
+    ctx->last_S = n_side;
+    if (out_points && !dev_out && *out_count > 0) {
+        RC(mr_out(ctx, out_points, d_out, (size_t)*out_count * 7 * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_extract_camera_center(const float camera[16], float out_center3[3])
+{
+    if (!camera || !out_center3) return MR_EINVAL;
+    mr_camera_center(camera, out_center3);
+    return MR_OK;
+}
+
+int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                          const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && out_count, "null argument");
+    CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
+    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
+    size_t N = ctx->N;
+    const uint8_t *d_main = (const uint8_t *)mr_in(ctx, main_frame, N, "in_main");
+    unsigned long long *vis_main = mr_buf<unsigned long long>(ctx, "vis_main", N);
+    float *depth = mr_buf<float>(ctx, "depth", N);
+    if (!d_main || !vis_main || !depth) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
+    Mat4 Pm = to_mat4(main_camera);
+    RC(k_raster(ctx, Pm, vis_main));            // recon.cpp:70  depth = render->depth(camera(fa))
+    RC(k_resolve_depth(ctx, vis_main, depth));
+    const float *d_flows[MR_MAX_SIDE];
+    for (int i = 0; i < n_side; i++) {           // recon.cpp:81
+        CHECK_ARG(ctx, side_frames[i], "null side frame");
+        const uint8_t *d_side = (const uint8_t *)mr_in(ctx, side_frames[i], N, "in_side");
+        float *flow = mr_buf<float>(ctx, flow_name(i), N * 4);
+        uint8_t *mixed = mr_buf<uint8_t>(ctx, mixed_name(i), N);
+        if (!d_side || !flow || !mixed) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
+        float *shd = nullptr;
+        RC(shadow_pass(ctx, side_cameras + 16 * i, &shd));                       // render_glx.cpp:272-329
+        RC(k_shade(ctx, vis_main, Pm, to_mat4(side_cameras + 16 * i), d_side, shd, nullptr, d_main, depth,
+                   mixed));                                                      // recon.cpp:85-86
+        RC(calculate_flow_dev(ctx, d_main, mixed, flow));                        // recon.cpp:89
+        d_flows[i] = flow;
+    }
+    bool dev_out = out_points && mr_is_device_ptr(out_points);
+    float *d_out = dev_out ? out_points : mr_buf<float>(ctx, "points", N * 7);
+    if (!d_out) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
+    RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_out, out_count));   // recon.cpp:114
+    ctx->last_S = n_side;
+    if (out_points && !dev_out && *out_count > 0) {
+        RC(mr_out(ctx, out_points, d_out, (size_t)*out_count * 7 * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+const float *mr_points_device(mr_context *ctx, int *out_count)
+{
+    if (!ctx) return nullptr;
+    if (out_count) *out_count = ctx->last_count;
+    return (const float *)mr_buf_raw(ctx, "points", 0);
+}
+const float *mr_last_depth_device(mr_context *ctx) { return ctx ? (const float *)mr_buf_raw(ctx, "depth", 0) : nullptr; }
+const float *mr_last_flow_device(mr_context *ctx, int side)
+{
+    if (!ctx || side < 0 || side >= MR_MAX_SIDE) return nullptr;
+    return (const float *)mr_buf_raw(ctx, flow_name(side), 0);
+}
+const uint8_t *mr_last_mixed_device(mr_context *ctx, int side)
+{
+    if (!ctx || side < 0 || side >= MR_MAX_SIDE) return nullptr;
+    return (const uint8_t *)mr_buf_raw(ctx, mixed_name(side), 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// common.cuh -- context, scratch arena and helpers shared by the kernels of
+// libmeshrecon_b200.so.  Everything here is sm_100a-only; there is no CPU fallback.
+//
+// Numerical contract: all kernels are compiled with -fmad=false and use IEEE
+// division / sqrt, and are written in the SAME operation order as the CPU oracle
+// (oracle/recon_oracle.c, oracle/cvprims.py), so integer/byte outputs and most
+// float outputs are bit-identical to it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/meshrecon_b200.h"
+
+#define MR_MAX_LEVELS 16
+
+struct Mat4 {
+    float m[16];
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+// Per-main-camera constants of triangulatePixels (util.cpp:85-89,99,174,209,219),
+// computed on the host exactly like the oracle's tri_ctx_init.
+struct TriConst {
+    float Pinv[16];
+    float M[MR_MAX_SIDE][16];
+    float B[MR_MAX_SIDE][6];
+    float pd[MR_MAX_SIDE][2];
+    float pw[MR_MAX_SIDE][4];
+    float centers[(MR_MAX_SIDE + 1) * 3];
+    int S;
+};
+
+struct mr_context {
+    int device = 0, W = 0, H = 0;
+    size_t N = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    std::map<std::string, DevBuf> bufs;
+    // mesh (Render::loadMesh)
+    int F = 0;
+    // last results
+    int last_count = 0;
+    int last_S = 0;
+    // pinned host scratch for small readbacks
+    int *h_count = nullptr;
+    // pyramid geometry of compare()
+    int n_levels = 0;
+    int lw[MR_MAX_LEVELS], lh[MR_MAX_LEVELS];
+    size_t loff[MR_MAX_LEVELS];
+    size_t pyr_total = 0;
+};
+
+extern thread_local std::string g_mr_create_error;
+
+int mr_fail(mr_context *ctx, int code, const char *what, const char *detail);
+
+#define MR_CUDA(ctx, call)                                                          \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) return mr_fail(ctx, MR_ECUDA, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define MR_LAUNCH_CHECK(ctx, name)                                                  \
+    do {                                                                            \
+        (ctx)->launches++;                                                          \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) return mr_fail(ctx, MR_ECUDA, name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// scratch arena: named device buffers, grown on demand, owned by the context
+void *mr_buf_raw(mr_context *ctx, const char *name, size_t bytes);
+template <class T>
+static inline T *mr_buf(mr_context *ctx, const char *name, size_t count)
+{
+    return (T *)mr_buf_raw(ctx, name, count * sizeof(T));
+}
+
+bool mr_is_device_ptr(const void *p);
+// Returns a device pointer holding `bytes` of `p`: `p` itself if it already lives on the
+// device, otherwise a staging buffer filled by an async H2D copy on the context stream.
+const void *mr_in(mr_context *ctx, const void *p, size_t bytes, const char *staging);
+// Copies a device result to the user's buffer (host: async D2H + stream sync by the caller).
+int mr_out(mr_context *ctx, void *dst, const void *src_dev, size_t bytes);
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- stage launchers (all enqueue on ctx->stream; device pointers only) ------------
+// raster.cu
+int k_load_mesh(mr_context *ctx, const float *d_vtx, const int32_t *d_faces, int F);
+int k_raster(mr_context *ctx, const Mat4 &P, unsigned long long *d_vis);
+int k_resolve_depth(mr_context *ctx, const unsigned long long *d_vis, float *d_depth);
+int k_dilate_shadow(mr_context *ctx, const float *d_depth_td, float *d_out_td);
+int k_shade(mr_context *ctx, const unsigned long long *d_vis_main, const Mat4 &Pmain, const Mat4 &Pside,
+            const uint8_t *d_side_frame, const float *d_shadow_td, uint8_t *d_rgb /*or null*/,
+            const uint8_t *d_main_frame /*or null*/, float *d_depth_inout /*or null*/, uint8_t *d_mixed /*or null*/);
+int k_mix_background(mr_context *ctx, const uint8_t *d_rgb, const uint8_t *d_bg, float *d_depth, uint8_t *d_out);
+// flow.cu
+int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4);
+int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const uint8_t *d_img, uint8_t *d_out);
+int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off);
+int k_zero_channel(mr_context *ctx, float *d_flow4, int channel);
+int mr_flow_init_tables(mr_context *ctx);
+// tri.cu
+int k_image_gradient(mr_context *ctx, const float *d_img, float *d_grad2);
+int k_triangulate(mr_context *ctx, const float *const *d_flows_host_array, int S, const float *Pmain, const float *cams,
+                  const float *d_depth, float *d_out7, int *out_count);
+void mr_tri_const_init(TriConst *c, const float *Pmain, const float *cams, int S);
+void mr_camera_center(const float *P, float *c3);

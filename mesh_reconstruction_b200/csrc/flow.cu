@@ -1,0 +1,360 @@
+// flow.cu -- CUDA replacement of calculateFlow (flow.cpp:19-42):
+//   cv::optflow::VariationalRefinement::calc (flow.cpp:29,32)  -> k_variational_refinement
+//   flowRemap  (util.cpp:390-403, cv::remap INTER_CUBIC 8U)     -> k_flow_remap
+//   compare    (util.cpp:332-361, absdiff/pyrDown/pyrUp)        -> k_compare
+//   mixChannels pack (flow.cpp:37-40)                           -> written in place into the 4-float record
+//
+// The arithmetic restates OpenCV's (see oracle/cvprims.py, which is bit-exact against the
+// cv2 binary for VR and remap) in the same operation order, with -fmad=false, so the flow
+// (u, v) is bit-identical to OpenCV's and the remapped image is byte-identical.
+//
+// This file holds the plane-per-stage implementation (one kernel per VR stage, state in
+// HBM/L2); vr_fused.cu holds the shared-memory tiled version built on the same device
+// functions.
+#include "common.cuh"
+#include "vr_math.cuh"
+
+// ======================================================================================
+// Variational refinement, stage kernels
+// ======================================================================================
+__global__ void __launch_bounds__(256) vr_derivs_kernel(const uint8_t *__restrict__ i0, const uint8_t *__restrict__ i1, int W, int H,
+                                                        VrPlanes p)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    VrDeriv d = vr_derivatives_at(i0, i1, W, H, x, y);
+    size_t i = (size_t)y * W + x;
+    p.Ix[i] = d.Ix; p.Iy[i] = d.Iy; p.Iz[i] = d.Iz; p.Ixx[i] = d.Ixx;
+    p.Ixy[i] = d.Ixy; p.Iyy[i] = d.Iyy; p.Ixz[i] = d.Ixz; p.Iyz[i] = d.Iyz;
+}
+
+__global__ void __launch_bounds__(256) vr_data_kernel(VrPlanes p, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    size_t i = (size_t)y * W + x;
+    VrDeriv d;
+    d.Ix = p.Ix[i]; d.Iy = p.Iy[i]; d.Iz = p.Iz[i]; d.Ixx = p.Ixx[i];
+    d.Ixy = p.Ixy[i]; d.Iyy = p.Iyy[i]; d.Ixz = p.Ixz[i]; d.Iyz = p.Iyz[i];
+    float du = p.du[i], dv = p.dv[i];
+    VrLin l = vr_data_term(d, du, dv);
+    p.A11[i] = l.A11; p.A12[i] = l.A12; p.A22[i] = l.A22; p.b1[i] = l.b1; p.b2[i] = l.b2;
+    // smoothness weight (forward differences, zero at the last column / row)
+    float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
+    if (x < W - 1) { ux = p.du[i + 1] - du; vx = p.dv[i + 1] - dv; }
+    if (y < H - 1) { uy = p.du[i + W] - du; vy = p.dv[i + W] - dv; }
+    p.ws[i] = vr_smooth_weight(ux, vx, uy, vy);
+}
+
+// one half-sweep of red-black SOR; color 0 = (x+y) even
+__global__ void __launch_bounds__(256) vr_sor_kernel(VrPlanes p, int W, int H, int color)
+{
+    int xh = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= H) return;
+    int x = 2 * xh + ((y + color) & 1);
+    if (x >= W) return;
+    size_t i = (size_t)y * W + x;
+    float wsP = p.ws[i];
+    float sR = (x < W - 1) ? wsP : 0.f, sD = (y < H - 1) ? wsP : 0.f;
+    float sL = (x > 0) ? p.ws[i - 1] : 0.f, sU = (y > 0) ? p.ws[i - W] : 0.f;
+    float duL = (x > 0) ? p.du[i - 1] : 0.f, duR = (x < W - 1) ? p.du[i + 1] : 0.f;
+    float duU = (y > 0) ? p.du[i - W] : 0.f, duD = (y < H - 1) ? p.du[i + W] : 0.f;
+    float dvL = (x > 0) ? p.dv[i - 1] : 0.f, dvR = (x < W - 1) ? p.dv[i + 1] : 0.f;
+    float dvU = (y > 0) ? p.dv[i - W] : 0.f, dvD = (y < H - 1) ? p.dv[i + W] : 0.f;
+    float A11 = vr_add_links(p.A11[i], sR, sL, sD, sU, color == 0);
+    float A22 = vr_add_links(p.A22[i], sR, sL, sD, sU, color == 0);
+    float du = p.du[i], dv = p.dv[i];
+    vr_sor_update(du, dv, sL, sR, sU, sD, duL, duR, duU, duD, dvL, dvR, dvU, dvD, p.b1[i], p.b2[i], p.A12[i], A11, A22);
+    p.du[i] = du;
+    p.dv[i] = dv;
+}
+
+__global__ void vr_pack_kernel(const float *__restrict__ du, const float *__restrict__ dv, size_t N, float *__restrict__ flow4)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float4 o = make_float4(du[i], dv[i], 0.f, 0.f);
+    ((float4 *)flow4)[i] = o;
+}
+
+int k_vr_fused(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4);  // vr_fused.cu
+extern int g_mr_vr_impl;  // 0 = plane-per-stage, 1 = fused tiles (default)
+
+static int vr_planes_impl(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
+{
+    int W = ctx->W, H = ctx->H;
+    size_t N = ctx->N;
+    float *base = mr_buf<float>(ctx, "vr_planes", N * 16);
+    if (!base) return mr_fail(ctx, MR_ENOMEM, "vr_planes", "alloc");
+    VrPlanes p;
+    float **f = (float **)&p;
+    for (int k = 0; k < 16; k++) f[k] = base + (size_t)k * N;
+    MR_CUDA(ctx, cudaMemsetAsync(p.du, 0, 2 * N * sizeof(float), ctx->stream));  // du, dv adjacent
+    dim3 b(32, 8), g(cdiv(W, 32), cdiv(H, 8));
+    vr_derivs_kernel<<<g, b, 0, ctx->stream>>>(d_i0, d_i1, W, H, p);
+    MR_LAUNCH_CHECK(ctx, "vr_derivs_kernel");
+    dim3 gs(cdiv((W + 1) / 2, 32), cdiv(H, 8));
+    for (int it = 0; it < VR_FIXED_POINT; it++) {
+        vr_data_kernel<<<g, b, 0, ctx->stream>>>(p, W, H);
+        MR_LAUNCH_CHECK(ctx, "vr_data_kernel");
+        for (int s = 0; s < VR_SOR; s++) {
+            vr_sor_kernel<<<gs, b, 0, ctx->stream>>>(p, W, H, 0);
+            MR_LAUNCH_CHECK(ctx, "vr_sor_kernel");
+            vr_sor_kernel<<<gs, b, 0, ctx->stream>>>(p, W, H, 1);
+            MR_LAUNCH_CHECK(ctx, "vr_sor_kernel");
+        }
+    }
+    vr_pack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(p.du, p.dv, N, d_flow4);
+    MR_LAUNCH_CHECK(ctx, "vr_pack_kernel");
+    return MR_OK;
+}
+
+int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
+{
+    if (g_mr_vr_impl == 1) return k_vr_fused(ctx, d_i0, d_i1, d_flow4);
+    return vr_planes_impl(ctx, d_i0, d_i1, d_flow4);
+}
+
+// ======================================================================================
+// cv::remap(8U, INTER_CUBIC, BORDER_CONSTANT 0)
+// ======================================================================================
+// 32x32 table of 4x4 Q15 weights, built on the host exactly like OpenCV's
+// initInterTab2D(INTER_CUBIC, fixpt) (oracle/cvprims.py::cubic_table_i16).
+static void cubic_coeffs(float t, float *c)
+{
+    const float A = -0.75f;
+    c[0] = ((A * (t + 1.f) - 5.f * A) * (t + 1.f) + 8.f * A) * (t + 1.f) - 4.f * A;
+    c[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+    float u = 1.f - t;
+    c[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static void build_cubic_table(int16_t *tab)
+{
+    float one[32][4];
+    for (int i = 0; i < 32; i++) cubic_coeffs((float)i / 32.f, one[i]);
+    for (int ay = 0; ay < 32; ay++)
+        for (int ax = 0; ax < 32; ax++) {
+            int it[4][4], isum = 0;
+            for (int k1 = 0; k1 < 4; k1++)
+                for (int k2 = 0; k2 < 4; k2++) {
+                    float v = one[ay][k1] * one[ax][k2];
+                    long r = lrintf(v * 32768.f);
+                    r = r < -32768 ? -32768 : (r > 32767 ? 32767 : r);
+                    it[k1][k2] = (int)r;
+                    isum += (int)r;
+                }
+            if (isum != 32768) {
+                int diff = isum - 32768, mk1 = 2, mk2 = 2, Mk1 = 2, Mk2 = 2;
+                for (int k1 = 2; k1 < 4; k1++)
+                    for (int k2 = 2; k2 < 4; k2++) {
+                        if (it[k1][k2] < it[mk1][mk2]) mk1 = k1, mk2 = k2;
+                        else if (it[k1][k2] > it[Mk1][Mk2]) Mk1 = k1, Mk2 = k2;
+                    }
+                if (diff < 0) it[Mk1][Mk2] -= diff;
+                else it[mk1][mk2] -= diff;
+            }
+            for (int k1 = 0; k1 < 4; k1++)
+                for (int k2 = 0; k2 < 4; k2++) tab[((ay * 32 + ax) * 4 + k1) * 4 + k2] = (int16_t)it[k1][k2];
+        }
+}
+
+int mr_flow_init_tables(mr_context *ctx)
+{
+    std::vector<int16_t> h(1024 * 16);
+    build_cubic_table(h.data());
+    int16_t *d = mr_buf<int16_t>(ctx, "cubic_tab", h.size());
+    if (!d) return mr_fail(ctx, MR_ENOMEM, "cubic_tab", "alloc");
+    MR_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+__device__ __forceinline__ int cv_round_sat(float v)
+{
+    // cvRound + saturate_cast<int>; |v| is far below 2^31 for any sane flow
+    if (!(v > -2147483648.0f && v < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rn(v);
+}
+
+__global__ void __launch_bounds__(256) remap_cubic_kernel(const float *__restrict__ flow, int stride, const uint8_t *__restrict__ img,
+                                                          const int16_t *__restrict__ tab, int W, int H, uint8_t *__restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    size_t i = (size_t)y * W + x;
+    float mx = flow[i * stride + 0] + (float)x;
+    float my = flow[i * stride + 1] + (float)y;
+    int sx = cv_round_sat(mx * 32.f), sy = cv_round_sat(my * 32.f);
+    int ix = sx >> 5, iy = sy >> 5;
+    ix = max(-32768, min(32767, ix)) - 1;
+    iy = max(-32768, min(32767, iy)) - 1;
+    const int16_t *w = tab + (((sy & 31) * 32 + (sx & 31)) << 4);
+    int acc = 0;
+#pragma unroll
+    for (int ky = 0; ky < 4; ky++) {
+        int yy = iy + ky;
+        if (yy < 0 || yy >= H) continue;
+        const uint8_t *r = img + (size_t)yy * W;
+#pragma unroll
+        for (int kx = 0; kx < 4; kx++) {
+            int xx = ix + kx;
+            if (xx < 0 || xx >= W) continue;
+            acc += (int)r[xx] * (int)w[ky * 4 + kx];
+        }
+    }
+    int v = (acc + (1 << 14)) >> 15;
+    out[i] = (uint8_t)max(0, min(255, v));
+}
+
+int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const uint8_t *d_img, uint8_t *d_out)
+{
+    int16_t *tab = mr_buf<int16_t>(ctx, "cubic_tab", 0);
+    dim3 b(32, 8), g(cdiv(ctx->W, 32), cdiv(ctx->H, 8));
+    remap_cubic_kernel<<<g, b, 0, ctx->stream>>>(d_flow, stride_floats, d_img, tab, ctx->W, ctx->H, d_out);
+    MR_LAUNCH_CHECK(ctx, "remap_cubic_kernel");
+    return MR_OK;
+}
+
+// ======================================================================================
+// compare(): L1 difference over a Gaussian pyramid (util.cpp:332-361)
+// ======================================================================================
+__device__ __forceinline__ int refl101(int i, int n)
+{
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+template <class T>
+__device__ __forceinline__ float pyr_down_at(const T *__restrict__ src, int w, int h, int X, int Y)
+{
+    float R[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const T *r = src + (size_t)refl101(2 * Y + k - 2, h) * w;
+        float r0 = (float)r[refl101(2 * X - 2, w)], r1 = (float)r[refl101(2 * X - 1, w)], r2 = (float)r[refl101(2 * X, w)];
+        float r3 = (float)r[refl101(2 * X + 1, w)], r4 = (float)r[refl101(2 * X + 2, w)];
+        R[k] = r2 * 6.f + ((r1 + r3) * 4.f + (r0 + r4));
+    }
+    return (((R[1] + R[3]) + R[2]) * 4.f + ((R[0] + R[4]) + (R[2] + R[2]))) * (1.f / 256.f);
+}
+
+// level l -> l+1 for both images, plus the L1 difference of the new level
+template <class T>
+__global__ void __launch_bounds__(256) pyr_down_pair_kernel(const T *__restrict__ a, const T *__restrict__ b, int w, int h,
+                                                            float *__restrict__ ao, float *__restrict__ bo, float *__restrict__ diff,
+                                                            int wo, int ho)
+{
+    int X = blockIdx.x * blockDim.x + threadIdx.x;
+    int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= wo || Y >= ho) return;
+    float va = pyr_down_at(a, w, h, X, Y), vb = pyr_down_at(b, w, h, X, Y);
+    size_t o = (size_t)Y * wo + X;
+    ao[o] = va;
+    bo[o] = vb;
+    diff[o] = fabsf(va - vb);
+}
+
+__global__ void absdiff_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t N, float *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out[i] = fabsf((float)a[i] - (float)b[i]);
+}
+
+__device__ __forceinline__ float pyr_up_row(const float *__restrict__ r, int w, int X)
+{
+    // horizontally up-sampled value at column X (0 <= X < 2w) of low-res row r
+    int x = X >> 1;
+    int xr = min(x + 1, w - 1);
+    if (X & 1) return (r[x] + r[xr]) * 4.f;
+    int xl = (w > 1) ? (x == 0 ? 1 : x - 1) : 0;
+    return (r[xl] + r[x] * 6.f) + r[xr];
+}
+
+// dst (W x H, level l) += pyrUp(src (w x h, level l+1)); writes into `out` with a pixel stride
+// (so that the last step can write straight into channel 2 of the flow record).
+__global__ void __launch_bounds__(256) pyr_up_add_kernel(const float *__restrict__ src, int w, int h, const float *dst,
+                                                         int W, int H, float *out, int out_stride, int out_off)
+{
+    int X = blockIdx.x * blockDim.x + threadIdx.x;
+    int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= W || Y >= H) return;
+    int Xc = min(X, 2 * w - 1), Yc = min(Y, 2 * h - 1);  // odd sizes duplicate the last column / row
+    int y = Yc >> 1;
+    int yd = min(y + 1, h - 1);
+    float v;
+    float r1 = pyr_up_row(src + (size_t)y * w, w, Xc);
+    float r2 = pyr_up_row(src + (size_t)yd * w, w, Xc);
+    if (Yc & 1) v = (r1 + r2) * (1.f / 16.f);
+    else {
+        int yu = (h > 1) ? (y == 0 ? 1 : y - 1) : 0;
+        float r0 = pyr_up_row(src + (size_t)yu * w, w, Xc);
+        v = ((r1 * 6.f + r0) + r2) * (1.f / 64.f);
+    }
+    size_t i = (size_t)Y * W + X;
+    out[i * out_stride + out_off] = dst[i] + v;
+}
+
+__global__ void strided_copy_kernel(const float *__restrict__ src, size_t N, float *__restrict__ out, int stride, int off)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i * stride + off] = src[i];
+}
+
+int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off)
+{
+    int L = ctx->n_levels;
+    float *pa = mr_buf<float>(ctx, "pyr_a", ctx->pyr_total);
+    float *pb = mr_buf<float>(ctx, "pyr_b", ctx->pyr_total);
+    float *pd = mr_buf<float>(ctx, "pyr_d", ctx->pyr_total);
+    if (!pa || !pb || !pd) return mr_fail(ctx, MR_ENOMEM, "pyr", "alloc");
+    dim3 b(32, 8);
+    absdiff_u8_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d_prev, d_next, ctx->N, pd);
+    MR_LAUNCH_CHECK(ctx, "absdiff_u8_kernel");
+    for (int l = 0; l + 1 < L; l++) {
+        int w = ctx->lw[l], h = ctx->lh[l], wo = ctx->lw[l + 1], ho = ctx->lh[l + 1];
+        dim3 g(cdiv(wo, 32), cdiv(ho, 8));
+        if (l == 0)
+            pyr_down_pair_kernel<uint8_t><<<g, b, 0, ctx->stream>>>(d_prev, d_next, w, h, pa + ctx->loff[1], pb + ctx->loff[1],
+                                                                    pd + ctx->loff[1], wo, ho);
+        else
+            pyr_down_pair_kernel<float><<<g, b, 0, ctx->stream>>>(pa + ctx->loff[l], pb + ctx->loff[l], w, h, pa + ctx->loff[l + 1],
+                                                                  pb + ctx->loff[l + 1], pd + ctx->loff[l + 1], wo, ho);
+        MR_LAUNCH_CHECK(ctx, "pyr_down_pair_kernel");
+    }
+    if (L == 1) {
+        // degenerate (min(H,W) <= 2): the result is the level-0 difference
+        strided_copy_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(pd, ctx->N, d_out, out_stride, out_off);
+        MR_LAUNCH_CHECK(ctx, "strided_copy_kernel");
+    }
+    for (int l = L - 2; l >= 0; l--) {
+        int W = ctx->lw[l], H = ctx->lh[l], w = ctx->lw[l + 1], h = ctx->lh[l + 1];
+        dim3 g(cdiv(W, 32), cdiv(H, 8));
+        if (l == 0)
+            pyr_up_add_kernel<<<g, b, 0, ctx->stream>>>(pd + ctx->loff[1], w, h, pd, W, H, d_out, out_stride, out_off);
+        else
+            pyr_up_add_kernel<<<g, b, 0, ctx->stream>>>(pd + ctx->loff[l + 1], w, h, pd + ctx->loff[l], W, H, pd + ctx->loff[l], 1, 0);
+        MR_LAUNCH_CHECK(ctx, "pyr_up_add_kernel");
+    }
+    return MR_OK;
+}
+
+__global__ void zero_channel_kernel(float *flow4, size_t N, int ch)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) flow4[4 * i + ch] = 0.f;
+}
+int k_zero_channel(mr_context *ctx, float *d_flow4, int channel)
+{
+    zero_channel_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d_flow4, ctx->N, channel);
+    MR_LAUNCH_CHECK(ctx, "zero_channel_kernel");
+    return MR_OK;
+}

@@ -188,7 +188,7 @@ void orc_raster(const float *soup, int F, const float *P, int W, int H, float *d
             for (int col = t.x0; col <= t.x1; col++) {
                 float X = ((float)col + 0.5f) * sx - 1.0f;
                 if (!edge_inside(t.e[0], X, Y) || !edge_inside(t.e[1], X, Y) || !edge_inside(t.e[2], X, Y)) continue;
-                float z = (t.zA * X + t.zB * Y) + t.zC;
+                float z = ((t.zA * X + t.zB * Y) + t.zC) + 0.0f; /* -0 -> +0 */
                 if (!(z >= -1.0f && z < 1.0f)) continue;
                 int idx = row * W + col;
                 if (z < depth[idx]) { depth[idx] = z; tri_idx[idx] = f; } /* GL_LESS, draw order */

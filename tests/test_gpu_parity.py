@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes binding) against the
+CPU oracle and the committed golden vectors.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): flow within 0.01 px (we assert bit-exact u, v and
+report it), 3-D points within 1e-4 of scene scale, byte/integer outputs bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import mesh_reconstruction_b200 as mr
+from mesh_reconstruction_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+f32 = np.float32
+FLOW_TOL_PX = 0.01          # north_star
+POINT_TOL_REL = 1e-4        # north_star: x scene scale
+VAR_TOL_REL = 1e-4          # variance: float-rounding level (OpenCV's own SIMD/scalar paths differ by this much)
+
+
+def _oracle():
+    import oracle  # noqa: F401  (checker only)
+    from oracle import flow, pipeline, render, tri
+    return flow, pipeline, render, tri
+
+
+def _points_close(got, ref, scale, what=""):
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    nan_g, nan_r = np.isnan(got).any(1), np.isnan(ref).any(1)
+    assert np.array_equal(nan_g, nan_r), what + ": NaN rows differ"
+    ok = ~nan_r
+    Xg = got[ok, :3].astype(np.float64) / got[ok, 3:4]
+    Xr = ref[ok, :3].astype(np.float64) / ref[ok, 3:4]
+    err = np.abs(Xg - Xr).max() if ok.any() else 0.0
+    assert err <= POINT_TOL_REL * scale, f"{what}: point error {err} > {POINT_TOL_REL * scale}"
+    return err
+
+
+def _normals_close(got, ref, what=""):
+    ok = ~(np.isnan(ref).any(1) | np.isnan(got).any(1))
+    ng, nr = got[ok, 4:7].astype(np.float64), ref[ok, 4:7].astype(np.float64)
+    lg, lr = np.linalg.norm(ng, axis=1), np.linalg.norm(nr, axis=1)
+    good = (lr > 0) & np.isfinite(lr) & np.isfinite(lg)
+    assert np.allclose(lg[good], lr[good], rtol=1e-3, atol=1e-12), what + ": normal length (pdf) differs"
+    cosang = np.sum(ng[good] * nr[good], 1) / (lg[good] * lr[good])
+    # direction: PCA smallest eigenvector; allow 1e-3 rad on 99.9 % of pixels (ill-conditioned windows excepted)
+    frac_bad = np.mean(cosang < np.cos(1e-3))
+    assert frac_bad < 1e-3, f"{what}: {frac_bad:.2e} of normals deviate > 1e-3 rad"
+    return frac_bad
+
+
+def test_glx_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "test_glx.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    r = mr.spawnRender(W, H)
+    r.loadMesh(synth.TEST_GLX_POINTS, synth.TEST_GLX_FACES)
+    assert np.array_equal(r.depth(synth.TEST_GLX_MVP), g["depth"])
+    assert np.array_equal(r.projected(synth.TEST_GLX_MVP, g["grid"], synth.TEST_GLX_SIDE_MVP), g["projected"])
+
+
+@pytest.mark.parametrize("name", ["scene_s2_96x72", "scene_s1_128x96"])
+def test_golden_stage_by_stage(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    W, H, fa, sides = int(g["W"]), int(g["H"]), int(g["fa"]), list(g["sides"])
+    frames, cams, scale = g["frames"], g["cameras"], float(g["scale"])
+    r = mr.spawnRender(W, H)
+    r.loadMesh(g["vertices"], g["faces"])
+    depth = r.depth(cams[fa])
+    assert np.array_equal(depth, g["depth0"])                                   # a2 bit-exact
+    flows = []
+    for i, fb in enumerate(sides):
+        proj = r.projected(cams[fa], frames[fb], cams[fb])
+        assert np.array_equal(proj, g["projected"][i])                          # a3 bit-exact
+        mixed = mr.mixBackground(proj, frames[fa], depth)
+        assert np.array_equal(mixed, g["mixed"][i])                             # a4 bit-exact (+ in-place depth)
+        flow = mr.calculateFlow(frames[fa], mixed)
+        ref = g["flows"][i]
+        d = np.abs(flow[..., :2] - ref[..., :2]).max()
+        assert d <= FLOW_TOL_PX
+        assert np.array_equal(flow[..., :2], ref[..., :2]), f"flow not bit-exact (max diff {d})"   # a5: cv2 bits
+        assert np.allclose(flow[..., 2], ref[..., 2], rtol=VAR_TOL_REL, atol=1e-4)                 # a7
+        assert not flow[..., 3].any()                                                                # quirk C2
+        flows.append(flow)
+    assert np.array_equal(depth, g["depth"])
+    # a10-a12 on the ORACLE's flows (isolates triangulation), then on our own flows
+    tri = mr.triangulatePixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"])
+    _points_close(tri, g["tri"], scale, "tri(oracle flows)")
+    _normals_close(tri, g["tri"], "tri(oracle flows)")
+    tri2 = mr.triangulatePixels(flows, cams[fa], [cams[s] for s in sides], depth)
+    _points_close(tri2, g["tri"], scale, "tri(own flows)")
+
+
+@pytest.mark.parametrize("name", ["scene_s2_96x72", "scene_s1_128x96"])
+def test_golden_fused_main_frame(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    W, H, fa, sides = int(g["W"]), int(g["H"]), int(g["fa"]), list(g["sides"])
+    r = mr.spawnRender(W, H)
+    r.loadMesh(g["vertices"], g["faces"])
+    tri = mr.process_main_frame(r, g["frames"][fa], g["cameras"][fa], [g["frames"][s] for s in sides],
+                                [g["cameras"][s] for s in sides])
+    _points_close(tri, g["tri"], float(g["scale"]), "fused")
+    _normals_close(tri, g["tri"], "fused")
+
+
+@pytest.mark.parametrize("W,H,S", [(320, 240, 1), (333, 247, 2), (640, 480, 4)])
+def test_seeded_scene_against_oracle(W, H, S):
+    """Sizes the oracle finishes in seconds; odd sizes exercise ragged tiles."""
+    _, pipeline, render, _ = _oracle()
+    n = 2 * S + 1 if S > 1 else 3
+    sc = synth.make_scene(W, H, n, seed=W, step=0.12, mesh_err=0.03, mesh_res=14)
+    frames = sc.frames()
+    fa = n // 2
+    sides = [i for i in range(n) if i != fa][:S]
+    ro = render.RenderOracle(W, H)
+    ro.loadMesh(sc.vertices, sc.faces)
+    ref, inter = pipeline.process_main_frame(ro, frames, sc.cameras, fa, sides, keep=True)
+    r = mr.spawnRender(W, H)
+    r.loadMesh(sc.vertices, sc.faces)
+    got = mr.process_main_frame(r, frames[fa], sc.cameras[fa], [frames[s] for s in sides], [sc.cameras[s] for s in sides])
+    # intermediates straight from the device
+    ctx = r.ctx
+    for i in range(S):
+        flow = _device_to_numpy(ctx.lib.mr_last_flow_device(ctx.h, i), (H, W, 4), np.float32)
+        assert np.array_equal(flow[..., :2], inter["flows"][i][..., :2])
+        assert np.allclose(flow[..., 2], inter["flows"][i][..., 2], rtol=VAR_TOL_REL, atol=1e-4)
+        mixed = _device_to_numpy(ctx.lib.mr_last_mixed_device(ctx.h, i), (H, W), np.uint8)
+        assert np.array_equal(mixed, inter["mixed"][i])
+    depth = _device_to_numpy(ctx.lib.mr_last_depth_device(ctx.h), (H, W), np.float32)
+    assert np.array_equal(depth, inter["depth"])
+    _points_close(got, ref, sc.scale, "pipeline")
+    _normals_close(got, ref, "pipeline")
+
+
+def _device_to_numpy(ptr, shape, dtype):
+    import torch
+    n = int(np.prod(shape))
+    tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+    torch.cuda.synchronize()
+    # wrap the library-owned device buffer without copying, then read it back
+    class _Ext:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dtype).str, "data": (int(ptr), True), "version": 3}
+    t = torch.as_tensor(_Ext(), device="cuda")
+    assert t.dtype == tdt
+    return t.cpu().numpy().reshape(shape).copy()
+
+
+def test_primitives_against_oracle():
+    flow, _, _, _ = _oracle()
+    rng = np.random.default_rng(0)
+    for (H, W) in [(61, 83), (240, 320), (135, 241)]:
+        a = (rng.random((H, W)) * 255).astype(np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-9, 9, (H, W)), 0, 255).astype(np.uint8)
+        fl = (rng.normal(size=(H, W, 2)) * 2.5).astype(f32)
+        fl[0, 0] = (-60, -60)
+        assert np.array_equal(mr.flowRemap(fl, a), flow.flow_remap(fl, a))                       # a6 bit-exact
+        fl4 = np.concatenate([fl, np.zeros((H, W, 2), f32)], -1)
+        assert np.array_equal(mr.flowRemap(fl4, a), flow.flow_remap(fl, a))
+        assert np.allclose(mr.compare(a, b), flow.compare(a, b), rtol=VAR_TOL_REL, atol=1e-4)    # a7
+        d = rng.random((H, W)).astype(f32)
+        d[rng.random((H, W)) < 0.2] = 1.0
+        g, gr = mr.imageGradient(d), flow.image_gradient(d)
+        assert np.allclose(g, gr, rtol=0, atol=2e-6) and (g != gr).mean() < 0.05                 # a8
+    c = synth.make_scene(64, 48, 3).cameras[1]
+    from oracle import native
+    ref = np.empty(3, f32)
+    native.lib().orc_camera_center(np.ascontiguousarray(c.ravel()), ref)
+    assert np.array_equal(mr.extractCameraCenter(c), ref)
+
+
+def test_flow_identical_frames_and_vr_impls_agree():
+    """Size-independent properties at the benchmark resolution (1080p): identical frames give an
+    exactly zero record; both VR implementations give identical bits."""
+    H, W = 1080, 1920
+    sc = synth.make_scene(W, H, 2, step=0.05)
+    a, b = sc.frame(0), sc.frame(1)
+    f = mr.calculateFlow(a, a)
+    assert not f.any()
+    lib = mr.load_library()
+    lib.mr_set_vr_impl(0)
+    f0 = mr.calculateFlow(a, b)
+    lib.mr_set_vr_impl(1)
+    try:
+        f1 = mr.calculateFlow(a, b)
+    except mr.MeshReconError:
+        f1 = None
+    finally:
+        lib.mr_set_vr_impl(0)
+    assert np.isfinite(f0).all() and np.abs(f0[..., :2]).max() < 5
+    if f1 is not None:
+        assert np.array_equal(f0, f1)
+    # the oracle on a 1080p crop-free pair (a few seconds of cv2)
+    flow, _, _, _ = _oracle()
+    ref = flow.calculate_flow(a, b)
+    assert np.array_equal(f0[..., :2], ref[..., :2])
+    assert np.allclose(f0[..., 2], ref[..., 2], rtol=VAR_TOL_REL, atol=1e-4)
+
+
+def test_error_behaviour():
+    r = mr.Render(32, 24, ctx=mr.api.Context(32, 24))
+    with pytest.raises(mr.MeshReconError) as e:
+        r.depth(np.eye(4, dtype=f32))                      # render before loadMesh
+    assert e.value.code == -4
+    a = np.zeros((24, 32), np.uint8)
+    with pytest.raises(mr.MeshReconError):
+        mr.calculateFlow(a, a, useFarneback=True)          # not implemented -> loud error, no fallback
+    r.loadMesh(np.zeros((0, 4), f32), np.zeros((0, 3), np.int32))   # empty mesh: everything is background
+    d = r.depth(np.eye(4, dtype=f32))
+    assert (d == 1.0).all()
