@@ -117,6 +117,14 @@ const uint8_t *mr_last_mixed_device(mr_context *ctx, int side);
  * kernels, 1 = fused shared-memory tile kernel (default).  Both produce identical bits. */
 int mr_set_vr_impl(int impl);
 
+/* Per-stage device timing for bench.py (CUDA events on the context stream).  Stages:
+ * 0 raster, 1 shade_mix, 2 variational_refinement, 3 cubic_remap, 4 pyramid_compare,
+ * 5 triangulate, 6 normals.  mr_profile_read synchronises, returns the milliseconds and kernel
+ * launches accumulated per stage since the last read, and resets them; returns the stage count. */
+int mr_profile_enable(mr_context *ctx, int on);
+int mr_profile_read(mr_context *ctx, double *ms_by_stage, uint64_t *launches_by_stage, int n);
+const char *mr_stage_name(int stage);
+
 /* Number of kernels this library launched on the context since creation (bench.py's
  * gpu_launches claim). */
 uint64_t mr_launch_count(const mr_context *ctx);

@@ -205,9 +205,12 @@ static int shadow_pass(mr_context *ctx, const float *projector, float **out)
     float *sh = mr_buf<float>(ctx, "shadow", ctx->N);
     float *shd = mr_buf<float>(ctx, "shadow_dil", ctx->N);
     if (!vis || !sh || !shd) return mr_fail(ctx, MR_ENOMEM, "shadow_pass", "alloc");
-    RC(k_raster(ctx, to_mat4(projector), vis));
-    RC(k_resolve_depth(ctx, vis, sh));
-    RC(k_dilate_shadow(ctx, sh, shd));
+    {
+        StageScope sc(ctx, ST_RASTER);
+        RC(k_raster(ctx, to_mat4(projector), vis));
+        RC(k_resolve_depth(ctx, vis, sh));
+        RC(k_dilate_shadow(ctx, sh, shd));
+    }
     *out = shd;
     return MR_OK;
 }
@@ -257,9 +260,18 @@ static int calculate_flow_dev(mr_context *ctx, const uint8_t *d_prev, const uint
 {
     uint8_t *remapped = mr_buf<uint8_t>(ctx, "remapped", ctx->N);
     if (!remapped) return mr_fail(ctx, MR_ENOMEM, "calculate_flow", "alloc");
-    RC(k_variational_refinement(ctx, d_prev, d_next, d_flow4));  // writes (u, v, 0, 0)
-    RC(k_flow_remap(ctx, d_flow4, 4, d_next, remapped));
-    RC(k_compare(ctx, d_prev, remapped, d_flow4, 4, 2));         // variance -> channel 2
+    {
+        StageScope sc(ctx, ST_VR);
+        RC(k_variational_refinement(ctx, d_prev, d_next, d_flow4));  // writes (u, v, 0, 0)
+    }
+    {
+        StageScope sc(ctx, ST_REMAP);
+        RC(k_flow_remap(ctx, d_flow4, 4, d_next, remapped));
+    }
+    {
+        StageScope sc(ctx, ST_COMPARE);
+        RC(k_compare(ctx, d_prev, remapped, d_flow4, 4, 2));         // variance -> channel 2
+    }
     return MR_OK;
 }
 
@@ -396,8 +408,11 @@ int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const floa
     float *depth = mr_buf<float>(ctx, "depth", N);
     if (!d_main || !vis_main || !depth) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
     Mat4 Pm = to_mat4(main_camera);
-    RC(k_raster(ctx, Pm, vis_main));            // recon.cpp:70  depth = render->depth(camera(fa))
-    RC(k_resolve_depth(ctx, vis_main, depth));
+    {
+        StageScope sc(ctx, ST_RASTER);
+        RC(k_raster(ctx, Pm, vis_main));            // recon.cpp:70  depth = render->depth(camera(fa))
+        RC(k_resolve_depth(ctx, vis_main, depth));
+    }
     const float *d_flows[MR_MAX_SIDE];
     for (int i = 0; i < n_side; i++) {           // recon.cpp:81
         CHECK_ARG(ctx, side_frames[i], "null side frame");
@@ -407,8 +422,11 @@ int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const floa
         if (!d_side || !flow || !mixed) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
         float *shd = nullptr;
         RC(shadow_pass(ctx, side_cameras + 16 * i, &shd));                       // render_glx.cpp:272-329
-        RC(k_shade(ctx, vis_main, Pm, to_mat4(side_cameras + 16 * i), d_side, shd, nullptr, d_main, depth,
-                   mixed));                                                      // recon.cpp:85-86
+        {
+            StageScope sc(ctx, ST_SHADE);
+            RC(k_shade(ctx, vis_main, Pm, to_mat4(side_cameras + 16 * i), d_side, shd, nullptr, d_main, depth,
+                       mixed));                                                  // recon.cpp:85-86
+        }
         RC(calculate_flow_dev(ctx, d_main, mixed, flow));                        // recon.cpp:89
         d_flows[i] = flow;
     }
@@ -422,6 +440,43 @@ int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const floa
         MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return MR_OK;
+}
+
+int mr_profile_enable(mr_context *ctx, int on)
+{
+    CHECK_CTX(ctx);
+    ctx->profile = on != 0;
+    return MR_OK;
+}
+
+int mr_profile_read(mr_context *ctx, double *ms_by_stage, uint64_t *launches_by_stage, int n)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        ctx->prof_ms[r.stage] += ms;
+        ctx->prof_launches[r.stage] += r.launches;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    for (int i = 0; i < n && i < ST_COUNT; i++) {
+        if (ms_by_stage) ms_by_stage[i] = ctx->prof_ms[i];
+        if (launches_by_stage) launches_by_stage[i] = ctx->prof_launches[i];
+        ctx->prof_ms[i] = 0;
+        ctx->prof_launches[i] = 0;
+    }
+    return ST_COUNT;
+}
+
+const char *mr_stage_name(int stage)
+{
+    static const char *names[ST_COUNT] = {"raster", "shade_mix", "variational_refinement", "cubic_remap", "pyramid_compare",
+                                          "triangulate", "normals"};
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
 }
 
 const float *mr_points_device(mr_context *ctx, int *out_count)

@@ -38,6 +38,14 @@ struct TriConst {
     int S;
 };
 
+// per-stage device timing (bench.py's roofline / stage breakdown); off by default
+enum MrStage { ST_RASTER = 0, ST_SHADE, ST_VR, ST_REMAP, ST_COMPARE, ST_TRI, ST_NORMALS, ST_COUNT };
+struct ProfRec {
+    int stage;
+    cudaEvent_t a, b;
+    uint64_t launches;
+};
+
 struct mr_context {
     int device = 0, W = 0, H = 0;
     size_t N = 0;
@@ -57,6 +65,40 @@ struct mr_context {
     int lw[MR_MAX_LEVELS], lh[MR_MAX_LEVELS];
     size_t loff[MR_MAX_LEVELS];
     size_t pyr_total = 0;
+    // profiling
+    bool profile = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[ST_COUNT] = {0};
+    uint64_t prof_launches[ST_COUNT] = {0};
+};
+
+// RAII: brackets a stage with CUDA events on the context stream when profiling is on
+struct StageScope {
+    mr_context *ctx;
+    ProfRec r;
+    bool on;
+    StageScope(mr_context *c, int stage) : ctx(c), on(c->profile)
+    {
+        if (!on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        r.stage = stage; r.a = get(); r.b = get(); r.launches = ctx->launches;
+        cudaEventRecord(r.a, ctx->stream);
+    }
+    void end()
+    {
+        if (!on) return;
+        on = false;
+        cudaEventRecord(r.b, ctx->stream);
+        r.launches = ctx->launches - r.launches;
+        ctx->prof_pending.push_back(r);
+    }
+    ~StageScope() { end(); }
 };
 
 extern thread_local std::string g_mr_create_error;

@@ -93,6 +93,34 @@ class Scene:
         y = o[1] + t * d[..., 1]
         return np.clip(np.rint(self.texture_at(x, y)), 0, 255).astype(np.uint8)
 
+    def frame_torch(self, i, device="cuda"):
+        """Same ray-cast as :meth:`frame`, evaluated with torch on the GPU (float64).  Used by
+        bench.py to synthesise long 1080p / 4K sequences quickly; not bit-identical to the
+        NumPy version (different libm), which is irrelevant for throughput inputs."""
+        import torch
+        W, H = self.width, self.height
+        dt = torch.float64
+        c = torch.as_tensor(self.cam2world[i], dtype=dt, device=device)
+        aspect = W / H
+        xs = ((torch.arange(W, dtype=dt, device=device) + 0.5) * 2.0 / W - 1.0) * (self.fov / 2)
+        ys = (1.0 - (torch.arange(H, dtype=dt, device=device) + 0.5) * 2.0 / H) * (self.fov / (2 * aspect))
+        dy, dx = torch.meshgrid(ys, xs, indexing="ij")
+        d = dx[..., None] * c[:3, 0] + dy[..., None] * c[:3, 1] + c[:3, 2]
+        o = c[:3, 3]
+        t = -o[2] / d[..., 2]
+        for _ in range(6):
+            x = o[0] + t * d[..., 0]
+            y = o[1] + t * d[..., 1]
+            sx, cx, sy, cy = torch.sin(self.fx * x), torch.cos(self.fx * x), torch.sin(self.fy * y), torch.cos(self.fy * y)
+            g = o[2] + t * d[..., 2] - self.amp * sx * sy
+            t = t - g / (d[..., 2] - self.amp * self.fx * cx * sy * d[..., 0] - self.amp * self.fy * sx * cy * d[..., 1])
+        x = o[0] + t * d[..., 0]
+        y = o[1] + t * d[..., 1]
+        v = torch.full_like(x, 128.0)
+        for kx, ky, ph, a in self.tex:
+            v = v + a * torch.sin(kx * x + ky * y + ph)
+        return torch.clamp(torch.round(v), 0, 255).to(torch.uint8)
+
     def frames(self, idx=None):
         idx = range(len(self.cameras)) if idx is None else idx
         return [self.frame(i) for i in idx]

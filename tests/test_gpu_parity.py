@@ -139,7 +139,7 @@ def _device_to_numpy(ptr, shape, dtype):
     torch.cuda.synchronize()
     # wrap the library-owned device buffer without copying, then read it back
     class _Ext:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dtype).str, "data": (int(ptr), True), "version": 3}
+        __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dtype).str, "data": (int(ptr), False), "version": 3}
     t = torch.as_tensor(_Ext(), device="cuda")
     assert t.dtype == tdt
     return t.cpu().numpy().reshape(shape).copy()
