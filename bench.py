@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pairs", type=int, default=8, help="frame pairs per GPU per step")
     ap.add_argument("--frames", type=int, default=300)
-    ap.add_argument("--cam-step", type=float, default=0.05)
+    ap.add_argument("--cam-step", type=float, default=0.006)
     ap.add_argument("--mesh-err", type=float, default=0.02)
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame pairs timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--vr-impl", type=int, default=None)
