@@ -184,21 +184,24 @@ def main():
     rows_dev = torch.empty((B, N, 7), dtype=torch.float32, device=dev)       # K7 writes straight into the send buffer
     rows_pin = torch.empty((N, 7), dtype=torch.float32).pin_memory()
     counts = torch.zeros(B, dtype=torch.int64)
-    gather_rows = torch.empty((world, B, N, 7), dtype=torch.float32, device=dev) if world > 1 else None
-    gather_counts = torch.empty((world, B), dtype=torch.int64, device=dev) if world > 1 else None
+    rows_flat = rows_dev.view(B * N, 7)
+    from mesh_reconstruction_b200.shard import allgather_points
 
     def pair(j):                      # j-th pair of this rank, cycling inside its block
         a = j % (n_local - 1)
         return a, a + 1
 
     def step_resident(s):
+        off = 0
         for b in range(B):
             a, c = pair(s * B + b)
-            counts[b] = mr.process_main_frame(render, frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
-                                              out=rows_dev[b], want_host=False)
+            # the normals kernel writes the rows straight into the all-gather send buffer at this rank's running offset
+            m = mr.process_main_frame(render, frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
+                                      out=rows_flat[off:], want_host=False)
+            counts[b] = m
+            off += m
         if world > 1:                 # the path's one exchange step: point rows -> every rank
-            dist.all_gather_into_tensor(gather_counts, counts.to(dev))
-            dist.all_gather_into_tensor(gather_rows, rows_dev)
+            allgather_points(rows_flat, off)
 
     def step_e2e(s):
         tot = 0

@@ -50,3 +50,60 @@ def test_extract_camera_center_is_host_side():
     sc = synth.make_scene(64, 48, 3)
     c = mr.extractCameraCenter(sc.cameras[0])
     assert np.allclose(c, sc.cam2world[0][:3, 3], rtol=1e-4, atol=1e-5)
+
+
+def _write_case(path, sc, frames, fa, sides):
+    import numpy as np
+    with open(path, "wb") as f:
+        np.array([sc.width, sc.height, len(sc.vertices), len(sc.faces), len(sides)], np.int32).tofile(f)
+        sc.vertices.astype(np.float32).tofile(f)
+        sc.faces.astype(np.int32).tofile(f)
+        sc.cameras[fa].astype(np.float32).tofile(f)
+        for s in sides:
+            sc.cameras[s].astype(np.float32).tofile(f)
+        frames[fa].tofile(f)
+        for s in sides:
+            frames[s].tofile(f)
+
+
+def test_cpp_host_mirror_fails_loudly_without_gpu(tmp_path):
+    """The C++ mirror of recon.hpp (recon_b200.hpp) drives recon.cpp's loop through the C ABI; on a
+    box without a GPU it must stop with the library's error, not compute on the CPU."""
+    import subprocess
+    import torch
+    from mesh_reconstruction_b200 import synth
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(ROOT, "mesh_reconstruction_b200", "host_mirror_test")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    sc = synth.make_scene(64, 48, 3, step=0.1, mesh_res=4)
+    frames = sc.frames()
+    _write_case(tmp_path / "in.bin", sc, frames, 1, [0, 2])
+    p = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert p.returncode == 3 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_matches_oracle(tmp_path):
+    import subprocess
+    import numpy as np
+    from mesh_reconstruction_b200 import synth
+    from oracle.pipeline import process_main_frame
+    from oracle.render import RenderOracle
+    exe = os.path.join(ROOT, "mesh_reconstruction_b200", "host_mirror_test")
+    sc = synth.make_scene(160, 120, 3, step=0.15, mesh_err=0.03, mesh_res=8)
+    frames = sc.frames()
+    _write_case(tmp_path / "in.bin", sc, frames, 1, [0, 2])
+    p = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    raw = np.fromfile(tmp_path / "out.bin", np.uint8)
+    M = int(raw[:4].view(np.int32)[0])
+    got = raw[4:].view(np.float32).reshape(M, 7)
+    ro = RenderOracle(160, 120)
+    ro.loadMesh(sc.vertices, sc.faces)
+    ref = process_main_frame(ro, frames, sc.cameras, 1, [0, 2])
+    assert got.shape == ref.shape
+    ok = ~np.isnan(ref).any(1)
+    assert np.array_equal(ok, ~np.isnan(got).any(1))
+    err = np.abs(got[ok, :3] / got[ok, 3:4] - ref[ok, :3] / ref[ok, 3:4]).max()
+    assert err <= 1e-4 * sc.scale

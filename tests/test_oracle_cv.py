@@ -133,3 +133,19 @@ def test_camera_center_matches_decompose_and_yaml_convention():
         L.orc_camera_center(np.ascontiguousarray(P4.ravel()), c)
         assert np.allclose(c, c_ref, rtol=2e-5, atol=2e-6)
         assert np.allclose(c, sc.cam2world[i][:3, 3], rtol=1e-4, atol=1e-5)
+
+
+def test_float_reciprocal_equals_double_rounded_reciprocal():
+    """`Mat /= s` multiplies by (float)(1.0/(double)s).  The CUDA kernels use the correctly rounded
+    float reciprocal instead; the two are identical for every float (double rounding is harmless
+    for reciprocals).  Exhaustive over all 2^23 mantissas of one binade plus random exponents."""
+    m = np.arange(1 << 23, dtype=np.uint32) | np.uint32(0x3F800000)
+    s = m.view(np.float32)
+    a = (1.0 / s.astype(np.float64)).astype(np.float32)           # reference form
+    # correctly rounded float reciprocal, computed exactly with integers: round(2^47 / M) etc. -> use float division
+    b = np.float32(1.0) / s                                         # IEEE float division, correctly rounded
+    assert np.array_equal(a, b)
+    rng = np.random.default_rng(0)
+    s2 = (rng.integers(0x00800000, 0x7F000000, 1 << 20, dtype=np.uint32)).view(np.float32)
+    with np.errstate(all="ignore"):
+        assert np.array_equal((1.0 / s2.astype(np.float64)).astype(np.float32), np.float32(1.0) / s2)
