@@ -114,7 +114,8 @@ const float *mr_last_flow_device(mr_context *ctx, int side);
 const uint8_t *mr_last_mixed_device(mr_context *ctx, int side);
 
 /* Debug / benchmarking knob (process-wide): 0 = plane-per-stage variational-refinement
- * kernels, 1 = fused shared-memory tile kernel (default).  Both produce identical bits. */
+ * kernels, 1 = fused shared-memory tile kernel with TMA-staged frames (default; falls back to
+ * plain loads when width % 16 != 0), 2 = fused kernel with plain loads.  Identical bits. */
 int mr_set_vr_impl(int impl);
 
 /* Per-stage device timing for bench.py (CUDA events on the context stream).  Stages:

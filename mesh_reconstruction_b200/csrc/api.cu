@@ -7,7 +7,8 @@
 #include "common.cuh"
 
 thread_local std::string g_mr_create_error;
-int g_mr_vr_impl = 0;
+int g_mr_vr_impl = 1;
+extern int g_mr_vr_tma;
 
 int mr_fail(mr_context *ctx, int code, const char *what, const char *detail)
 {
@@ -157,10 +158,12 @@ int mr_synchronize(mr_context *ctx)
     return MR_OK;
 }
 
-// debug / benchmarking knob: 0 = plane-per-stage VR kernels, 1 = fused tile kernel
+// debug / benchmarking knob: 0 = plane-per-stage VR kernels, 1 = fused tile kernel with TMA staging
+// (default), 2 = fused tile kernel with plain loads
 int mr_set_vr_impl(int impl)
 {
     g_mr_vr_impl = impl ? 1 : 0;
+    g_mr_vr_tma = impl == 2 ? 0 : 1;
     return MR_OK;
 }
 

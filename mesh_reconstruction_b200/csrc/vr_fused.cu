@@ -1,6 +1,329 @@
-// vr_fused.cu -- placeholder until the fused tile kernel lands (see flow.cu).
+// vr_fused.cu -- fused shared-memory tile kernel for OpenCV's VariationalRefinement (flow.cpp:29,32).
+//
+// One launch per fixed-point iteration.  A CTA owns an OTW x OTH output tile and evaluates the whole
+// iteration (derivatives -> robust data term -> smoothness weights -> 5 red-black SOR sweeps) on the
+// tile plus a 10-pixel halo, so that nothing but du/dv crosses HBM between iterations:
+//
+//   region I (tile + 11/16): the two 8-bit frames  -> shared memory, staged by TMA (cp.async.bulk.tensor.2d
+//                                                     + mbarrier).  The out-of-image halo is zero-filled by
+//                                                     the TMA unit and never read (taps are clamped).
+//   region D (tile + 10)   : Ix, Iy, Iz, du, dv, w -> shared memory, red/black SPLIT layout: each colour of
+//                                                     the checkerboard is a dense array, so every neighbour
+//                                                     access of a warp is unit-stride (no bank conflicts)
+//   region C (tile +  9)   : A11, A12, A22, b1, b2 -> REGISTERS of the owning thread (7 column pairs each)
+//
+// Dependency radius of one iteration is 10 (one pixel per SOR half-sweep), +1 for the weights, +2 for
+// the derivatives; halo pixels keep being updated with stale neighbours after their values stop
+// mattering, and that contamination travels inwards one pixel per half-sweep, i.e. it never reaches
+// the tile.  Arithmetic and operation order are those of vr_math.cuh (bit-exact vs cv2), -fmad=false.
+//
+// Thread layout: 42 x 12.  Thread (tx, ty) owns column pair tx (D-local columns 2tx, 2tx+1) of rows
+// 1 + ty + 12k, k = 0..6; the row parity -- hence which column of the pair is red -- is fixed per
+// thread, and every shared-memory address is `base + k * const`.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
-int k_vr_fused(mr_context *ctx, const uint8_t *, const uint8_t *, float *)
+#include "vr_math.cuh"
+
+namespace {
+
+constexpr int HALO = 10;
+constexpr int OTW = 64, OTH = 64;                          // output tile
+constexpr int DW = OTW + 2 * HALO, DH = OTH + 2 * HALO;    // region D (origin = tile - 10)
+constexpr int NP = DW / 2;                                 // column pairs per row == entries per colour per row
+constexpr int IX_OFF = 16, IY_OFF = HALO + 1;              // image tile origin = tile - (16, 11): x must be 16-byte aligned for TMA
+constexpr int IPITCH = 96, IH = DH + 2;                    // image tile: 96 bytes x 86 rows
+constexpr int TY = 12;                                     // thread rows
+constexpr int NT = 512;                                    // threads per CTA (NP * TY = 504 active in the pair phases)
+constexpr int SLOTS = (DH - 2 + TY - 1) / TY;              // rows owned per thread (7)
+constexpr int PLANE = DH * NP;                             // floats per colour per plane
+static_assert(DW % 2 == 0 && NP * TY <= NT && (TY % 2) == 0, "thread layout");
+static_assert(IX_OFF + OTW + HALO + 1 <= IPITCH, "image tile width");
+
+struct Smem {
+    alignas(128) uint8_t i0[IH * IPITCH];
+    alignas(128) uint8_t i1[IH * IPITCH];
+    float Ix[2][PLANE], Iy[2][PLANE], Iz[2][PLANE];        // [colour][row * NP + idx]; colour 0 = red = (x + y) even
+    float du[2][PLANE], dv[2][PLANE], ws[2][PLANE];
+    alignas(8) unsigned long long bar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FIRST, bool LAST, bool USE_TMA>
+__global__ void __launch_bounds__(NT, 1) vr_fused_kernel(const uint8_t *__restrict__ g0, const uint8_t *__restrict__ g1,
+                                                         const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                                                         const float *__restrict__ du_in, const float *__restrict__ dv_in,
+                                                         float *__restrict__ du_out, float *__restrict__ dv_out,
+                                                         float4 *__restrict__ flow4, int W, int H)
 {
-    return mr_fail(ctx, MR_EINVAL, "k_vr_fused", "fused VR kernel not built");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int gx0 = blockIdx.x * OTW, gy0 = blockIdx.y * OTH;
+    const int dx0 = gx0 - HALO, dy0 = gy0 - HALO;          // image coords of D-local (0, 0): both even
+    const int ix0 = gx0 - IX_OFF, iy0 = gy0 - IY_OFF;      // image coords of I-local (0, 0)
+
+    // ---- stage the two frames ----------------------------------------------------------------------------
+    if (USE_TMA) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s.bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s.bar)), "r"(2 * IH * IPITCH) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_u32(s.i0)), "l"(&tm0), "r"(ix0), "r"(iy0), "r"(smem_u32(&s.bar)) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_u32(s.i1)), "l"(&tm1), "r"(ix0), "r"(iy0), "r"(smem_u32(&s.bar)) : "memory");
+        }
+    } else {
+        for (int e = tid; e < IH * IPITCH; e += NT) {
+            int r = e / IPITCH, c = e % IPITCH;
+            int x = ix0 + c, y = iy0 + r;
+            uint8_t a = 0, b = 0;
+            if (x >= 0 && x < W && y >= 0 && y < H) { a = g0[(size_t)y * W + x]; b = g1[(size_t)y * W + x]; }
+            s.i0[e] = a;
+            s.i1[e] = b;
+        }
+    }
+    // ---- du / dv of region D from the previous iteration (zero on the first one and outside the image) ----
+    for (int e = tid; e < DH * DW; e += NT) {
+        int r = e / DW, c = e % DW;
+        int x = dx0 + c, y = dy0 + r;
+        float u = 0.f, v = 0.f;
+        if (!FIRST && x >= 0 && x < W && y >= 0 && y < H) { u = du_in[(size_t)y * W + x]; v = dv_in[(size_t)y * W + x]; }
+        int col = (r + c) & 1, idx = r * NP + (c >> 1);
+        s.du[col][idx] = u;
+        s.dv[col][idx] = v;
+    }
+    if (USE_TMA) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&s.bar)) : "memory");
+    }
+    __syncthreads();
+
+    // ---- first derivatives + smoothness weights on D -----------------------------------------------------------
+    for (int e = tid; e < DH * DW; e += NT) {
+        int r = e / DW, c = e % DW;
+        int x = dx0 + c, y = dy0 + r;
+        int col = (r + c) & 1, idx = r * NP + (c >> 1), o = col ^ 1;
+        float ix = 0.f, iy = 0.f, iz = 0.f, w = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const int lx = x - ix0, ly = y - iy0;
+            const int lxl = vr_clampi(x - 1, W) - ix0, lxr = vr_clampi(x + 1, W) - ix0;
+            const int lyu = vr_clampi(y - 1, H) - iy0, lyd = vr_clampi(y + 1, H) - iy0;
+            auto A = [&](int xx, int yy) { int i = yy * IPITCH + xx; return 0.5f * (float)s.i0[i] + 0.5f * (float)s.i1[i]; };
+            ix = A(lxr, ly) - A(lxl, ly);
+            iy = A(lx, lyd) - A(lx, lyu);
+            int i = ly * IPITCH + lx;
+            iz = (float)s.i1[i] - (float)s.i0[i];
+            if (r < DH - 1 && c < DW - 1) {
+                float u = s.du[col][idx], v = s.dv[col][idx];
+                float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
+                int ir = r * NP + ((c + 1) >> 1), id = idx + NP;
+                if (x < W - 1) { ux = s.du[o][ir] - u; vx = s.dv[o][ir] - v; }
+                if (y < H - 1) { uy = s.du[o][id] - u; vy = s.dv[o][id] - v; }
+                w = vr_smooth_weight(ux, vx, uy, vy);
+            }
+        }
+        s.Ix[col][idx] = ix;
+        s.Iy[col][idx] = iy;
+        s.Iz[col][idx] = iz;
+        s.ws[col][idx] = w;
+    }
+    __syncthreads();
+
+    // ---- per-thread constants of the pair phases ------------------------------------------------------------------
+    const int tx = tid % NP, ty = tid / NP;
+    const bool tact = tid < NP * TY;
+    const int par = (1 + ty) & 1;                           // parity of every row this thread owns
+    const int base = (1 + ty) * NP + tx;                    // split index of slot 0 (both colours)
+    const int ystart = dy0 + 1 + ty;
+    int nl[2], xs[2];                                       // per colour: index of the left neighbour (other colour), image x
+    bool cact[2], hasL[2], hasR[2];
+#pragma unroll
+    for (int col = 0; col < 2; col++) {
+        int c = 2 * tx + (col == 0 ? par : 1 - par);
+        xs[col] = dx0 + c;
+        nl[col] = (col == 0) ? tx + par - 1 : tx - par;     // relative to the row start
+        nl[col] -= tx;                                      // -> offset from the own index (-1, 0)
+        cact[col] = tact && c >= 1 && c <= DW - 2 && xs[col] >= 0 && xs[col] < W;
+        hasL[col] = xs[col] > 0;
+        hasR[col] = xs[col] < W - 1;
+    }
+
+    // ---- data term of the owned pixels -> registers ---------------------------------------------------------------
+    float A11[SLOTS][2], A12[SLOTS][2], A22[SLOTS][2], B1[SLOTS][2], B2[SLOTS][2];
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const int idx = base + k * TY * NP;
+        const int y = ystart + k * TY;
+        const bool ract = (1 + ty + k * TY) <= DH - 2 && y >= 0 && y < H;
+        const bool hasU = y > 0, hasD = y < H - 1;
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            const int o = col ^ 1;
+            VrLin l;
+            l.A11 = l.A22 = 1.f; l.A12 = l.b1 = l.b2 = 0.f;
+            if (ract && cact[col]) {
+                const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
+                VrDeriv d;
+                d.Ix = s.Ix[col][idx];
+                d.Iy = s.Iy[col][idx];
+                d.Iz = s.Iz[col][idx];
+                // second derivatives: central differences of the first ones, border-replicated
+                float ixl = hasL[col] ? s.Ix[o][iL] : d.Ix, ixr = hasR[col] ? s.Ix[o][iR] : d.Ix;
+                float ixu = hasU ? s.Ix[o][iU] : d.Ix, ixd = hasD ? s.Ix[o][iD] : d.Ix;
+                float iyu = hasU ? s.Iy[o][iU] : d.Iy, iyd = hasD ? s.Iy[o][iD] : d.Iy;
+                float izl = hasL[col] ? s.Iz[o][iL] : d.Iz, izr = hasR[col] ? s.Iz[o][iR] : d.Iz;
+                float izu = hasU ? s.Iz[o][iU] : d.Iz, izd = hasD ? s.Iz[o][iD] : d.Iz;
+                d.Ixx = ixr - ixl;
+                d.Ixy = ixd - ixu;
+                d.Iyy = iyd - iyu;
+                d.Ixz = izr - izl;
+                d.Iyz = izd - izu;
+                l = vr_data_term(d, s.du[col][idx], s.dv[col][idx]);
+                // link weights -> diagonal (colour-dependent accumulation order)
+                float wsP = s.ws[col][idx];
+                float sR = hasR[col] ? wsP : 0.f, sD = hasD ? wsP : 0.f;
+                float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = hasU ? s.ws[o][iU] : 0.f;
+                l.A11 = vr_add_links(l.A11, sR, sL, sD, sU, col == 0);
+                l.A22 = vr_add_links(l.A22, sR, sL, sD, sU, col == 0);
+            }
+            A11[k][col] = l.A11; A12[k][col] = l.A12; A22[k][col] = l.A22; B1[k][col] = l.b1; B2[k][col] = l.b2;
+        }
+    }
+
+    // ---- red-black SOR ---------------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int sweep = 0; sweep < VR_SOR; sweep++) {
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            const int o = col ^ 1;
+            if (cact[col]) {
+#pragma unroll
+                for (int k = 0; k < SLOTS; k++) {
+                    const int idx = base + k * TY * NP;
+                    const int y = ystart + k * TY;
+                    const bool ract = (1 + ty + k * TY) <= DH - 2 && y >= 0 && y < H;
+                    if (ract) {
+                        const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
+                        float wsP = s.ws[col][idx];
+                        float sR = hasR[col] ? wsP : 0.f, sD = (y < H - 1) ? wsP : 0.f;
+                        float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = (y > 0) ? s.ws[o][iU] : 0.f;
+                        float u = s.du[col][idx], v = s.dv[col][idx];
+                        vr_sor_update(u, v, sL, sR, sU, sD, s.du[o][iL], s.du[o][iR], s.du[o][iU], s.du[o][iD], s.dv[o][iL], s.dv[o][iR],
+                                      s.dv[o][iU], s.dv[o][iD], B1[k][col], B2[k][col], A12[k][col], A11[k][col], A22[k][col]);
+                        s.du[col][idx] = u;
+                        s.dv[col][idx] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- write the tile -----------------------------------------------------------------------------------------------
+    for (int e = tid; e < OTH * OTW; e += NT) {
+        int tyy = e / OTW, txx = e % OTW;
+        int x = gx0 + txx, y = gy0 + tyy;
+        if (x < W && y < H) {
+            int r = tyy + HALO, c = txx + HALO;
+            int col = (r + c) & 1, idx = r * NP + (c >> 1);
+            float u = s.du[col][idx], v = s.dv[col][idx];
+            size_t g = (size_t)y * W + x;
+            if (LAST) flow4[g] = make_float4(u, v, 0.f, 0.f);
+            else { du_out[g] = u; dv_out[g] = v; }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D uint8 tensor map with a (96 x 86) box.  TMA needs: base and row pitch multiples of 16 bytes, and
+// (measured on B200: "illegal instruction" otherwise) the box's x origin a multiple of 16 bytes, which
+// the kernel guarantees (tile origin - 16).
+bool make_u8_map(CUtensorMap *tm, const uint8_t *base, int W, int H)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc || (W % 16) != 0 || ((uintptr_t)base % 16) != 0) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    cuuint64_t strides[1] = {(cuuint64_t)W};
+    cuuint32_t box[2] = {(cuuint32_t)IPITCH, (cuuint32_t)IH};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool FIRST, bool LAST, bool USE_TMA>
+int launch(mr_context *ctx, const uint8_t *g0, const uint8_t *g1, const CUtensorMap &tm0, const CUtensorMap &tm1, const float *du_in,
+           const float *dv_in, float *du_out, float *dv_out, float4 *flow4)
+{
+    auto kern = vr_fused_kernel<FIRST, LAST, USE_TMA>;
+    static bool attr = false;
+    if (!attr) {
+        MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr = true;
+    }
+    dim3 grid(cdiv(ctx->W, OTW), cdiv(ctx->H, OTH));
+    kern<<<grid, NT, sizeof(Smem), ctx->stream>>>(g0, g1, tm0, tm1, du_in, dv_in, du_out, dv_out, flow4, ctx->W, ctx->H);
+    MR_LAUNCH_CHECK(ctx, "vr_fused_kernel");
+    return MR_OK;
+}
+
+template <bool USE_TMA>
+int run(mr_context *ctx, const uint8_t *g0, const uint8_t *g1, const CUtensorMap &tm0, const CUtensorMap &tm1, float *d_flow4)
+{
+    size_t N = ctx->N;
+    float *buf = mr_buf<float>(ctx, "vr_pingpong", N * 4);
+    if (!buf) return mr_fail(ctx, MR_ENOMEM, "vr_pingpong", "alloc");
+    float *duA = buf, *dvA = buf + N, *duB = buf + 2 * N, *dvB = buf + 3 * N;
+    float4 *f4 = (float4 *)d_flow4;
+    int rc = launch<true, false, USE_TMA>(ctx, g0, g1, tm0, tm1, nullptr, nullptr, duA, dvA, f4);
+    if (rc) return rc;
+    for (int it = 1; it < VR_FIXED_POINT - 1; it++) {
+        rc = launch<false, false, USE_TMA>(ctx, g0, g1, tm0, tm1, duA, dvA, duB, dvB, f4);
+        if (rc) return rc;
+        float *t = duA; duA = duB; duB = t;
+        t = dvA; dvA = dvB; dvB = t;
+    }
+    return launch<false, true, USE_TMA>(ctx, g0, g1, tm0, tm1, duA, dvA, nullptr, nullptr, f4);
+}
+
+}  // namespace
+
+int g_mr_vr_tma = 1;   // 1 = stage the frames with TMA when the layout allows it, 0 = plain loads
+
+int k_vr_fused(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
+{
+    static_assert(VR_FIXED_POINT >= 2, "fixed point iterations");
+    CUtensorMap tm0, tm1;
+    memset(&tm0, 0, sizeof(tm0));
+    memset(&tm1, 0, sizeof(tm1));
+    bool tma = g_mr_vr_tma && make_u8_map(&tm0, d_i0, ctx->W, ctx->H) && make_u8_map(&tm1, d_i1, ctx->W, ctx->H);
+    if (tma) return run<true>(ctx, d_i0, d_i1, tm0, tm1, d_flow4);
+    return run<false>(ctx, d_i0, d_i1, tm0, tm1, d_flow4);
 }

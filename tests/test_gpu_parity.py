@@ -177,18 +177,17 @@ def test_flow_identical_frames_and_vr_impls_agree():
     f = mr.calculateFlow(a, a)
     assert not f.any()
     lib = mr.load_library()
-    lib.mr_set_vr_impl(0)
-    f0 = mr.calculateFlow(a, b)
-    lib.mr_set_vr_impl(1)
     try:
-        f1 = mr.calculateFlow(a, b)
-    except mr.MeshReconError:
-        f1 = None
-    finally:
         lib.mr_set_vr_impl(0)
+        f0 = mr.calculateFlow(a, b)          # plane-per-stage kernels
+        lib.mr_set_vr_impl(2)
+        f2 = mr.calculateFlow(a, b)          # fused tile kernel, plain loads
+        lib.mr_set_vr_impl(1)
+        f1 = mr.calculateFlow(a, b)          # fused tile kernel, TMA-staged frames (default)
+    finally:
+        lib.mr_set_vr_impl(1)
     assert np.isfinite(f0).all() and np.abs(f0[..., :2]).max() < 5
-    if f1 is not None:
-        assert np.array_equal(f0, f1)
+    assert np.array_equal(f0, f2) and np.array_equal(f0, f1)
     # the oracle on a 1080p crop-free pair (a few seconds of cv2)
     flow, _, _, _ = _oracle()
     ref = flow.calculate_flow(a, b)
