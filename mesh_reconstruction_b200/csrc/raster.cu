@@ -194,18 +194,30 @@ int k_resolve_depth(mr_context *ctx, const unsigned long long *d_vis, float *d_d
 //   HF[i][j]  = max(o[i][j-1], o[i][j], o[i][j+1])    i >= 1
 //   out[i][j] = max(HF[i-1][j], HF[i][j], HF[i+1][j]) (rows clipped to [0, H-1]); columns 0 and W-1 untouched.
 // Equivalence with the sequential loop is tested in tests/test_oracle_path.py.
-__global__ void row_prefix_min_kernel(const float *__restrict__ row, int W, float *__restrict__ out)
+__global__ void __launch_bounds__(1024) row_prefix_min_kernel(const float *__restrict__ row, int W, float *__restrict__ out)
 {
-    // single block; W is at most a few thousand
-    extern __shared__ float s[];
-    for (int i = threadIdx.x; i < W; i += blockDim.x) s[i] = row[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = s[0];
-        for (int i = 0; i < W; i++) {
-            if (s[i] < m) m = s[i];
-            out[i] = m;
+    // single block, inclusive prefix-min over W <= 1024 * items values: warp shuffles + one smem pass
+    __shared__ float warp_min[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float carry = __int_as_float(0x7f800000);  // +inf
+    for (int base = 0; base < W; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        float v = (i < W) ? row[i] : __int_as_float(0x7f800000);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            float t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d && t < v) v = t;
         }
+        if (lane == 31) warp_min[wid] = v;
+        __syncthreads();
+        float pre = carry;
+        for (int w = 0; w < wid; w++) pre = fminf(pre, warp_min[w]);
+        if (pre < v) v = pre;
+        if (i < W) out[i] = v;
+        float tot = carry;
+        for (int w = 0; w < nw; w++) tot = fminf(tot, warp_min[w]);
+        __syncthreads();
+        carry = tot;
     }
 }
 
@@ -247,7 +259,7 @@ int k_dilate_shadow(mr_context *ctx, const float *d_depth_td, float *d_out_td)
 {
     int W = ctx->W, H = ctx->H;
     float *pm = mr_buf<float>(ctx, "rowmin", (size_t)W);
-    row_prefix_min_kernel<<<1, 256, W * sizeof(float), ctx->stream>>>(d_depth_td + (size_t)(H - 1) * W, W, pm);
+    row_prefix_min_kernel<<<1, 1024, 0, ctx->stream>>>(d_depth_td + (size_t)(H - 1) * W, W, pm);
     MR_LAUNCH_CHECK(ctx, "row_prefix_min_kernel");
     dim3 b(32, 8), g(cdiv(W, 32), cdiv(H, 8));
     dilate_kernel<<<g, b, 0, ctx->stream>>>(d_depth_td, pm, W, H, d_out_td);

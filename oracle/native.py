@@ -40,7 +40,7 @@ def lib():
     L.orc_camera_center.argtypes = [f32p, f32p]
     L.orc_jacobi3.argtypes = [f32p, f32p, f32p]
     L.orc_pca_normal.argtypes = [f32p, C.c_int, f32p, f32p]
-    L.orc_normals_compact.argtypes = [f32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, f32p]
+    L.orc_normals_compact.argtypes = [f32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, f32p, C.c_void_p]
     L.orc_normals_compact.restype = C.c_int
     _lib = L
     return L

@@ -24,8 +24,10 @@ def process_main_frame(render: RenderOracle, frames, cameras, fa, sides, use_far
             inter["projected"].append(proj)
             inter["mixed"].append(mixed)
             inter["flows"].append(flow)
-    tri = triangulate_pixels(flows, cameras[fa], cams, depth)           # recon.cpp:114
     if keep:
+        tri, evals = triangulate_pixels(flows, cameras[fa], cams, depth, return_evals=True)   # recon.cpp:114
         inter["depth"] = depth
+        inter["evals"] = evals
         return tri, inter
+    tri = triangulate_pixels(flows, cameras[fa], cams, depth)           # recon.cpp:114
     return tri

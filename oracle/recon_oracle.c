@@ -687,7 +687,7 @@ void orc_pca_normal(const float *pts, int K, float *normal3, float *evals3)
 /* pixel (C9).                                                                */
 /* ------------------------------------------------------------------------ */
 int orc_normals_compact(const float *dense5, const uint8_t *valid, int W, int H, const float *Pmain,
-                        const float *cams, int S, float *out7)
+                        const float *cams, int S, float *out7, float *evals_out /* M*4 (l0,l1,l2,K) or NULL: test diagnostics */)
 {
     const int radius = 10;
     int nc = S + 1;
@@ -727,8 +727,9 @@ int orc_normals_compact(const float *dense5, const uint8_t *valid, int W, int H,
                     }
                 }
                 float n[3];
+                float ev[3] = {0.f, 0.f, 0.f};
                 if (K >= 3) {
-                    orc_pca_normal(nb, K, n, 0);
+                    orc_pca_normal(nb, K, n, ev);
                     float dot = 0.f;
                     for (int c = 0; c < nc; c++) {
                         double d = 0;
@@ -749,6 +750,10 @@ int orc_normals_compact(const float *dense5, const uint8_t *valid, int W, int H,
                 double nn = sqrt((double)n[0] * n[0] + (double)n[1] * n[1] + (double)n[2] * n[2]);
                 float sc = (float)((double)pdf * (1.0 / nn));
                 float *o = out7 + 7 * (size_t)pid[i];
+                if (evals_out) {
+                    float *e = evals_out + 4 * (size_t)pid[i];
+                    e[0] = ev[0]; e[1] = ev[1]; e[2] = ev[2]; e[3] = (float)K;
+                }
                 for (int q = 0; q < 4; q++) o[q] = dense5[5 * i + q];
                 for (int q = 0; q < 3; q++) o[4 + q] = n[q] * sc;
             }

@@ -28,15 +28,21 @@ def triangulate_dense(flows, main_camera, cameras, depth, gradient=None, want_it
     return dense, valid
 
 
-def triangulate_pixels(flows, main_camera, cameras, depth, gradient=None):
+def triangulate_pixels(flows, main_camera, cameras, depth, gradient=None, return_evals=False):
     """``triangulatePixels``: M x 7 float32 rows (x, y, z, w, nx, ny, nz) in
-    row-major pixel order."""
+    row-major pixel order.  With ``return_evals`` also the PCA eigenvalues and neighbour count
+    of every row (M x 4: l0 >= l1 >= l2, K), a diagnostic the parity tests use to tell
+    well-conditioned normals from ill-conditioned ones."""
     H, W = depth.shape
     S = len(flows)
     dense, valid = triangulate_dense(flows, main_camera, cameras, depth, gradient)
     cams = np.ascontiguousarray(np.stack(cameras), f32).reshape(S, 16)
     out = np.empty((int(valid.sum()), 7), f32)
+    evals = np.zeros((max(len(out), 1), 4), f32) if return_evals else None
     m = native.lib().orc_normals_compact(dense, valid, W, H, np.ascontiguousarray(main_camera, f32).reshape(16), cams, S,
-                                         out if len(out) else np.empty((1, 7), f32))
+                                         out if len(out) else np.empty((1, 7), f32),
+                                         evals.ctypes.data if return_evals else None)
     assert m == len(out)
+    if return_evals:
+        return out, evals[:len(out)]
     return out

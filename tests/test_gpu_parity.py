@@ -37,16 +37,29 @@ def _points_close(got, ref, scale, what=""):
     return err
 
 
-def _normals_close(got, ref, what=""):
+def _normals_close(got, ref, what="", evals=None):
+    """Normal parity.  Lengths carry the pdf and must agree to 1e-3 relative.  Directions are the
+    smallest eigenvector of a 3x3 covariance the REFERENCE accumulates from float-rounded centred
+    samples (relative noise ~1e-7), so its own direction is only defined to about
+    1e-7 * l_max / (l_mid - l_min): we require 1e-3 rad wherever that conditioning bound allows it
+    (gap >= 1e-3 * l_max, K >= 3) and merely unit-consistency elsewhere; without eigenvalues we
+    fall back to 99 % of the pixels."""
     ok = ~(np.isnan(ref).any(1) | np.isnan(got).any(1))
     ng, nr = got[ok, 4:7].astype(np.float64), ref[ok, 4:7].astype(np.float64)
     lg, lr = np.linalg.norm(ng, axis=1), np.linalg.norm(nr, axis=1)
     good = (lr > 0) & np.isfinite(lr) & np.isfinite(lg)
     assert np.allclose(lg[good], lr[good], rtol=1e-3, atol=1e-12), what + ": normal length (pdf) differs"
     cosang = np.sum(ng[good] * nr[good], 1) / (lg[good] * lr[good])
-    # direction: PCA smallest eigenvector; allow 1e-3 rad on 99.9 % of pixels (ill-conditioned windows excepted)
-    frac_bad = np.mean(cosang < np.cos(1e-3))
-    assert frac_bad < 1e-3, f"{what}: {frac_bad:.2e} of normals deviate > 1e-3 rad"
+    bad = cosang < np.cos(1e-3)
+    if evals is not None:
+        ev = evals[ok][good].astype(np.float64)
+        well = (ev[:, 3] >= 3) & ((ev[:, 1] - ev[:, 2]) >= 1e-3 * np.maximum(ev[:, 0], 1e-30))
+        assert well.mean() > 0.5, what + ": too few well-conditioned normals to test"
+        frac_bad = np.mean(bad[well])
+        assert frac_bad <= 1e-4, f"{what}: {frac_bad:.2e} of well-conditioned normals deviate > 1e-3 rad"
+        return frac_bad
+    frac_bad = np.mean(bad)
+    assert frac_bad < 1e-2, f"{what}: {frac_bad:.2e} of normals deviate > 1e-3 rad"
     return frac_bad
 
 
@@ -86,7 +99,10 @@ def test_golden_stage_by_stage(golden_dir, name):
     # a10-a12 on the ORACLE's flows (isolates triangulation), then on our own flows
     tri = mr.triangulatePixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"])
     _points_close(tri, g["tri"], scale, "tri(oracle flows)")
-    _normals_close(tri, g["tri"], "tri(oracle flows)")
+    _, _, _, otri = _oracle()
+    ref_tri, evals = otri.triangulate_pixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"], return_evals=True)
+    assert np.array_equal(ref_tri, g["tri"], equal_nan=True)
+    _normals_close(tri, g["tri"], "tri(oracle flows)", evals)
     tri2 = mr.triangulatePixels(flows, cams[fa], [cams[s] for s in sides], depth)
     _points_close(tri2, g["tri"], scale, "tri(own flows)")
 
@@ -129,7 +145,7 @@ def test_seeded_scene_against_oracle(W, H, S):
     depth = _device_to_numpy(ctx.lib.mr_last_depth_device(ctx.h), (H, W), np.float32)
     assert np.array_equal(depth, inter["depth"])
     _points_close(got, ref, sc.scale, "pipeline")
-    _normals_close(got, ref, "pipeline")
+    _normals_close(got, ref, "pipeline", inter["evals"])
 
 
 def _device_to_numpy(ptr, shape, dtype):
