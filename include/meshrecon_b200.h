@@ -104,6 +104,16 @@ int mr_extract_camera_center(const float camera[16], float out_center3[3]);
 int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                           const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
                           int *out_count);
+/* Pipelined variant for HOST (ideally pinned) out_points: returns as soon as the rows are complete on
+ * the device and *out_count is known; their device->host copy into out_points runs on a second
+ * stream and overlaps the NEXT call's compute (two internal row buffers are ping-ponged).  The caller
+ * alternates between (at least) two host buffers; a buffer's contents are valid after mr_wait_copies()
+ * or mr_synchronize().  With a device out_points it behaves exactly like mr_process_main_frame. */
+int mr_process_main_frame_async(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                                const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
+                                int *out_count);
+/* Block until every outstanding row copy of mr_process_main_frame_async has landed. */
+int mr_wait_copies(mr_context *ctx);
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */
 const float *mr_points_device(mr_context *ctx, int *out_count);

@@ -64,6 +64,8 @@ def load_library():
     L.mr_triangulate_pixels.argtypes = [vp, fpp, C.c_int, vp, vp, vp, vp, ip]
     L.mr_extract_camera_center.argtypes = [vp, vp]
     L.mr_process_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
+    L.mr_process_main_frame_async.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
+    L.mr_wait_copies.argtypes = [vp]
     L.mr_points_device.argtypes = [vp, ip]
     L.mr_points_device.restype = vp
     L.mr_last_depth_device.argtypes = [vp]
@@ -122,6 +124,9 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.mr_synchronize(self.h))
+
+    def wait_copies(self):
+        self.check(self.lib.mr_wait_copies(self.h))
 
     @property
     def stream(self):
@@ -287,10 +292,12 @@ def triangulatePixels(flows, mainCamera, cameras, depth, device=0):
     return out[:m.value].copy()
 
 
-def process_main_frame(render, main_frame, main_camera, side_frames, side_cameras, out=None, want_host=True):
+def process_main_frame(render, main_frame, main_camera, side_frames, side_cameras, out=None, want_host=True, async_copy=False):
     """One iteration of the reference's outer loop (recon.cpp:65-119), fused and
     device-resident.  Returns the M x 7 rows (NumPy) or, with ``want_host=False``, just M
-    (rows stay on the device: ``Context.lib.mr_points_device``)."""
+    (rows stay on the device: ``Context.lib.mr_points_device``).  With ``async_copy`` (host
+    ``out``) the D2H copy of the rows overlaps the next call: alternate two pinned ``out`` buffers
+    and call ``render.ctx.wait_copies()`` before reading them; the call then returns M."""
     ctx = render.ctx
     S = len(side_frames)
     keep = [_ptr(f, np.uint8) for f in side_frames]
@@ -306,7 +313,8 @@ def process_main_frame(render, main_frame, main_camera, side_frames, side_camera
         po = out.ctypes.data
     else:
         po = None
-    ctx.check(ctx.lib.mr_process_main_frame(ctx.h, pf, pm, S, arr, cams.ctypes.data, po, C.byref(m)))
-    if want_host and not _is_torch(out):
+    fn = ctx.lib.mr_process_main_frame_async if async_copy else ctx.lib.mr_process_main_frame
+    ctx.check(fn(ctx.h, pf, pm, S, arr, cams.ctypes.data, po, C.byref(m)))
+    if want_host and not async_copy and not _is_torch(out):
         return out[:m.value]
     return m.value

@@ -142,6 +142,10 @@ void mr_destroy(mr_context *ctx)
     for (auto &kv : ctx->bufs)
         if (kv.second.p) cudaFree(kv.second.p);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int i = 0; i < 2; i++) if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
+    for (auto &r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -155,6 +159,17 @@ int mr_synchronize(mr_context *ctx)
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) MR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+    return MR_OK;
+}
+
+int mr_wait_copies(mr_context *ctx)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    if (ctx->copy_stream) MR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending[0] = ctx->copy_pending[1] = false;
     return MR_OK;
 }
 
@@ -397,8 +412,9 @@ int mr_extract_camera_center(const float camera[16], float out_center3[3])
     return MR_OK;
 }
 
-int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
-                          const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
+static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                                   const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count,
+                                   bool async_copy)
 {
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
@@ -434,15 +450,47 @@ int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const floa
         d_flows[i] = flow;
     }
     bool dev_out = out_points && mr_is_device_ptr(out_points);
-    float *d_out = dev_out ? out_points : mr_buf<float>(ctx, "points", N * 7);
+    const bool pipelined = async_copy && out_points && !dev_out;
+    float *d_out;
+    int slot = 0;
+    if (dev_out) d_out = out_points;
+    else if (pipelined) {
+        // ping-pong row buffers: the copy of slot s may still be in flight while slot s^1 is computed
+        if (!ctx->copy_stream) {
+            MR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
+        }
+        slot = ctx->rows_cur;
+        d_out = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
+        if (d_out && ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
+    } else
+        d_out = mr_buf<float>(ctx, "points", N * 7);
     if (!d_out) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
-    RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_out, out_count));   // recon.cpp:114
+    RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_out, out_count));   // recon.cpp:114 (syncs the stream)
     ctx->last_S = n_side;
-    if (out_points && !dev_out && *out_count > 0) {
+    if (pipelined) {
+        if (*out_count > 0)
+            MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_out, (size_t)*out_count * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        MR_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+        ctx->copy_pending[slot] = true;
+        ctx->rows_cur = slot ^ 1;
+    } else if (out_points && !dev_out && *out_count > 0) {
         RC(mr_out(ctx, out_points, d_out, (size_t)*out_count * 7 * sizeof(float)));
         MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return MR_OK;
+}
+
+int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                          const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
+{
+    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, false);
+}
+
+int mr_process_main_frame_async(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                                const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
+{
+    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, true);
 }
 
 int mr_profile_enable(mr_context *ctx, int on)

@@ -65,6 +65,11 @@ struct mr_context {
     int lw[MR_MAX_LEVELS], lh[MR_MAX_LEVELS];
     size_t loff[MR_MAX_LEVELS];
     size_t pyr_total = 0;
+    // pipelined device->host copies of point rows (mr_process_main_frame_async)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    int rows_cur = 0;
     // profiling
     bool profile = false;
     std::vector<ProfRec> prof_pending;
