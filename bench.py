@@ -48,33 +48,35 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons (NVML, every few ms) while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], 0, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.15)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    self.reasons |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                time.sleep(0.004)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["unavailable: " + getattr(self, "err", "no samples")]}
+        sm = sorted(self.sm)
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_sm,
+                "reasons": [n for b, n in bits.items() if self.reasons & b], "samples": len(sm)}
 
 
 def cpu_reference_pairs(scene, frames, pairs, threads):
@@ -181,27 +183,44 @@ def main():
     render.loadMesh(scene.vertices, scene.faces)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    rows_dev = torch.empty((B, N, 7), dtype=torch.float32, device=dev)       # K7 writes straight into the send buffer
+    nbuf = 2 if world > 1 else 1
+    rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
     rows_pin = [torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
     counts = torch.zeros(B, dtype=torch.int64)
-    rows_flat = rows_dev.view(B * N, 7)
-    from mesh_reconstruction_b200.shard import allgather_points
+    rows_flat = [r.view(B * N, 7) for r in rows_dev]
+    gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    gather_counts = [torch.empty((world * B,), dtype=torch.int64, device=dev) for _ in range(nbuf)] if world > 1 else None
+    pending = [None] * nbuf
 
     def pair(j):                      # j-th pair of this rank, cycling inside its block
         a = j % (n_local - 1)
         return a, a + 1
 
+    def wait_pending(k):
+        # make the LIBRARY stream (not torch's current stream) wait for the collective that still reads buffer k
+        if pending[k] is not None:
+            with torch.cuda.stream(lib_stream):
+                for h in pending[k]:
+                    h.wait()
+            pending[k] = None
+
     def step_resident(s):
+        k = s % nbuf
+        wait_pending(k)
         off = 0
         for b in range(B):
             a, c = pair(s * B + b)
             # the normals kernel writes the rows straight into the all-gather send buffer at this rank's running offset
             m = mr.process_main_frame(render, frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
-                                      out=rows_flat[off:], want_host=False)
+                                      out=rows_flat[k][off:], want_host=False)
             counts[b] = m
             off += m
-        if world > 1:                 # the path's one exchange step: point rows -> every rank
-            allgather_points(rows_flat, off)
+        if world > 1:
+            # the path's one exchange step: point rows + counts -> every rank, over NCCL/NVLink, ASYNC so that it
+            # overlaps the next step's compute (double-buffered send/receive buffers; rows are complete: the call above synced)
+            h1 = dist.all_gather_into_tensor(gather_counts[k], counts.to(dev, non_blocking=False), async_op=True)
+            h2 = dist.all_gather_into_tensor(gather_rows[k], rows_flat[k], async_op=True)
+            pending[k] = (h1, h2)
 
     def step_e2e(s):
         # host frames in (pinned, H2D inside the call), point rows out to pinned host memory every pair; the D2H
@@ -221,6 +240,8 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, first):
+        for k in range(nbuf):
+            wait_pending(k)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
@@ -228,7 +249,8 @@ def main():
         for s in range(steps):
             fn(first + s)
         if world > 1:
-            lib_stream.wait_stream(torch.cuda.current_stream())
+            for k in range(nbuf):
+                wait_pending(k)           # the exchange of every timed step completes inside the timed region
         e1.record(lib_stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -291,7 +313,7 @@ def main():
             "config": {"workload": f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S=1 (BASELINE config 4)",
                        "pairs_per_step_per_gpu": B, "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
                        "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
-                       "exchange": "nccl all_gather_into_tensor of point rows" if world > 1 else "none (single GPU)"},
+                       "exchange": "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step" if world > 1 else "none (single GPU)"},
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": int(m_mean * 28 * B),
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
