@@ -136,6 +136,10 @@ int mr_profile_enable(mr_context *ctx, int on);
 int mr_profile_read(mr_context *ctx, double *ms_by_stage, uint64_t *launches_by_stage, int n);
 const char *mr_stage_name(int stage);
 
+/* Test hook: runs the host build of the kernels' 3x3 symmetric eigen-solver (cv::eigen restatement,
+ * csrc/jacobi3.cuh).  cov6 = c00,c01,c02,c11,c12,c22; eigenvalues descending, eigenvectors in rows. */
+int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9]);
+
 /* Number of kernels this library launched on the context since creation (bench.py's
  * gpu_launches claim). */
 uint64_t mr_launch_count(const mr_context *ctx);

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "jacobi3.cuh"
 
 thread_local std::string g_mr_create_error;
 int g_mr_vr_impl = 1;
@@ -528,6 +529,14 @@ const char *mr_stage_name(int stage)
     static const char *names[ST_COUNT] = {"raster", "shade_mix", "variational_refinement", "cubic_remap", "pyramid_compare",
                                           "triangulate", "normals"};
     return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
+}
+
+// test hook: the host instantiation of the device's 3x3 Jacobi (same source, jacobi3.cuh)
+int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9])
+{
+    if (!cov6 || !evals3 || !evecs9) return MR_EINVAL;
+    mr_jacobi3(cov6, evals3, evecs9);
+    return MR_OK;
 }
 
 const float *mr_points_device(mr_context *ctx, int *out_count)

@@ -51,6 +51,103 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Data term + red-black SOR for the pixels a thread owns.  INTERIOR tiles (tile + halo entirely inside
+// the image) drop every border predicate at compile time.
+template <bool INTERIOR>
+__device__ __forceinline__ void pair_phases(Smem &s, const int tid, const int dx0, const int dy0, const int W, const int H)
+{
+    // ---- per-thread constants of the pair phases ------------------------------------------------------------------
+    const int tx = tid % NP, ty = tid / NP;
+    const bool tact = tid < NP * TY;
+    const int par = (1 + ty) & 1;                           // parity of every row this thread owns
+    const int base = (1 + ty) * NP + tx;                    // split index of slot 0 (both colours)
+    const int ystart = dy0 + 1 + ty;
+    int nl[2], xs[2];                                       // per colour: index of the left neighbour (other colour), image x
+    bool cact[2], hasL[2], hasR[2];
+#pragma unroll
+    for (int col = 0; col < 2; col++) {
+        int c = 2 * tx + (col == 0 ? par : 1 - par);
+        xs[col] = dx0 + c;
+        nl[col] = (col == 0) ? tx + par - 1 : tx - par;     // relative to the row start
+        nl[col] -= tx;                                      // -> offset from the own index (-1, 0)
+        cact[col] = tact && c >= 1 && c <= DW - 2 && (INTERIOR || (xs[col] >= 0 && xs[col] < W));
+        hasL[col] = INTERIOR || xs[col] > 0;
+        hasR[col] = INTERIOR || xs[col] < W - 1;
+    }
+
+    // ---- data term of the owned pixels -> registers ---------------------------------------------------------------
+    float A11[SLOTS][2], A12[SLOTS][2], A22[SLOTS][2], B1[SLOTS][2], B2[SLOTS][2];
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const int idx = base + k * TY * NP;
+        const int y = ystart + k * TY;
+        const bool ract = (1 + ty + k * TY) <= DH - 2 && (INTERIOR || (y >= 0 && y < H));
+        const bool hasU = INTERIOR || y > 0, hasD = INTERIOR || y < H - 1;
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            const int o = col ^ 1;
+            VrLin l;
+            l.A11 = l.A22 = 1.f; l.A12 = l.b1 = l.b2 = 0.f;
+            if (ract && cact[col]) {
+                const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
+                VrDeriv d;
+                d.Ix = s.Ix[col][idx];
+                d.Iy = s.Iy[col][idx];
+                d.Iz = s.Iz[col][idx];
+                // second derivatives: central differences of the first ones, border-replicated
+                float ixl = hasL[col] ? s.Ix[o][iL] : d.Ix, ixr = hasR[col] ? s.Ix[o][iR] : d.Ix;
+                float ixu = hasU ? s.Ix[o][iU] : d.Ix, ixd = hasD ? s.Ix[o][iD] : d.Ix;
+                float iyu = hasU ? s.Iy[o][iU] : d.Iy, iyd = hasD ? s.Iy[o][iD] : d.Iy;
+                float izl = hasL[col] ? s.Iz[o][iL] : d.Iz, izr = hasR[col] ? s.Iz[o][iR] : d.Iz;
+                float izu = hasU ? s.Iz[o][iU] : d.Iz, izd = hasD ? s.Iz[o][iD] : d.Iz;
+                d.Ixx = ixr - ixl;
+                d.Ixy = ixd - ixu;
+                d.Iyy = iyd - iyu;
+                d.Ixz = izr - izl;
+                d.Iyz = izd - izu;
+                l = vr_data_term(d, s.du[col][idx], s.dv[col][idx]);
+                // link weights -> diagonal (colour-dependent accumulation order)
+                float wsP = s.ws[col][idx];
+                float sR = hasR[col] ? wsP : 0.f, sD = hasD ? wsP : 0.f;
+                float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = hasU ? s.ws[o][iU] : 0.f;
+                l.A11 = vr_add_links(l.A11, sR, sL, sD, sU, col == 0);
+                l.A22 = vr_add_links(l.A22, sR, sL, sD, sU, col == 0);
+            }
+            A11[k][col] = l.A11; A12[k][col] = l.A12; A22[k][col] = l.A22; B1[k][col] = l.b1; B2[k][col] = l.b2;
+        }
+    }
+
+    // ---- red-black SOR ---------------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int sweep = 0; sweep < VR_SOR; sweep++) {
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            const int o = col ^ 1;
+            if (cact[col]) {
+#pragma unroll
+                for (int k = 0; k < SLOTS; k++) {
+                    const int idx = base + k * TY * NP;
+                    const int y = ystart + k * TY;
+                    const bool ract = (1 + ty + k * TY) <= DH - 2 && (INTERIOR || (y >= 0 && y < H));
+                    if (ract) {
+                        const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
+                        float wsP = s.ws[col][idx];
+                        float sR = hasR[col] ? wsP : 0.f, sD = (INTERIOR || y < H - 1) ? wsP : 0.f;
+                        float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = (INTERIOR || y > 0) ? s.ws[o][iU] : 0.f;
+                        float u = s.du[col][idx], v = s.dv[col][idx];
+                        vr_sor_update(u, v, sL, sR, sU, sD, s.du[o][iL], s.du[o][iR], s.du[o][iU], s.du[o][iD], s.dv[o][iL], s.dv[o][iR],
+                                      s.dv[o][iU], s.dv[o][iD], B1[k][col], B2[k][col], A12[k][col], A11[k][col], A22[k][col]);
+                        s.du[col][idx] = u;
+                        s.dv[col][idx] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+}
+
 template <bool FIRST, bool LAST, bool USE_TMA>
 __global__ void __launch_bounds__(NT, 1) vr_fused_kernel(const uint8_t *__restrict__ g0, const uint8_t *__restrict__ g1,
                                                          const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -138,95 +235,10 @@ __global__ void __launch_bounds__(NT, 1) vr_fused_kernel(const uint8_t *__restri
     }
     __syncthreads();
 
-    // ---- per-thread constants of the pair phases ------------------------------------------------------------------
-    const int tx = tid % NP, ty = tid / NP;
-    const bool tact = tid < NP * TY;
-    const int par = (1 + ty) & 1;                           // parity of every row this thread owns
-    const int base = (1 + ty) * NP + tx;                    // split index of slot 0 (both colours)
-    const int ystart = dy0 + 1 + ty;
-    int nl[2], xs[2];                                       // per colour: index of the left neighbour (other colour), image x
-    bool cact[2], hasL[2], hasR[2];
-#pragma unroll
-    for (int col = 0; col < 2; col++) {
-        int c = 2 * tx + (col == 0 ? par : 1 - par);
-        xs[col] = dx0 + c;
-        nl[col] = (col == 0) ? tx + par - 1 : tx - par;     // relative to the row start
-        nl[col] -= tx;                                      // -> offset from the own index (-1, 0)
-        cact[col] = tact && c >= 1 && c <= DW - 2 && xs[col] >= 0 && xs[col] < W;
-        hasL[col] = xs[col] > 0;
-        hasR[col] = xs[col] < W - 1;
-    }
-
-    // ---- data term of the owned pixels -> registers ---------------------------------------------------------------
-    float A11[SLOTS][2], A12[SLOTS][2], A22[SLOTS][2], B1[SLOTS][2], B2[SLOTS][2];
-#pragma unroll
-    for (int k = 0; k < SLOTS; k++) {
-        const int idx = base + k * TY * NP;
-        const int y = ystart + k * TY;
-        const bool ract = (1 + ty + k * TY) <= DH - 2 && y >= 0 && y < H;
-        const bool hasU = y > 0, hasD = y < H - 1;
-#pragma unroll
-        for (int col = 0; col < 2; col++) {
-            const int o = col ^ 1;
-            VrLin l;
-            l.A11 = l.A22 = 1.f; l.A12 = l.b1 = l.b2 = 0.f;
-            if (ract && cact[col]) {
-                const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
-                VrDeriv d;
-                d.Ix = s.Ix[col][idx];
-                d.Iy = s.Iy[col][idx];
-                d.Iz = s.Iz[col][idx];
-                // second derivatives: central differences of the first ones, border-replicated
-                float ixl = hasL[col] ? s.Ix[o][iL] : d.Ix, ixr = hasR[col] ? s.Ix[o][iR] : d.Ix;
-                float ixu = hasU ? s.Ix[o][iU] : d.Ix, ixd = hasD ? s.Ix[o][iD] : d.Ix;
-                float iyu = hasU ? s.Iy[o][iU] : d.Iy, iyd = hasD ? s.Iy[o][iD] : d.Iy;
-                float izl = hasL[col] ? s.Iz[o][iL] : d.Iz, izr = hasR[col] ? s.Iz[o][iR] : d.Iz;
-                float izu = hasU ? s.Iz[o][iU] : d.Iz, izd = hasD ? s.Iz[o][iD] : d.Iz;
-                d.Ixx = ixr - ixl;
-                d.Ixy = ixd - ixu;
-                d.Iyy = iyd - iyu;
-                d.Ixz = izr - izl;
-                d.Iyz = izd - izu;
-                l = vr_data_term(d, s.du[col][idx], s.dv[col][idx]);
-                // link weights -> diagonal (colour-dependent accumulation order)
-                float wsP = s.ws[col][idx];
-                float sR = hasR[col] ? wsP : 0.f, sD = hasD ? wsP : 0.f;
-                float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = hasU ? s.ws[o][iU] : 0.f;
-                l.A11 = vr_add_links(l.A11, sR, sL, sD, sU, col == 0);
-                l.A22 = vr_add_links(l.A22, sR, sL, sD, sU, col == 0);
-            }
-            A11[k][col] = l.A11; A12[k][col] = l.A12; A22[k][col] = l.A22; B1[k][col] = l.b1; B2[k][col] = l.b2;
-        }
-    }
-
-    // ---- red-black SOR ---------------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (int sweep = 0; sweep < VR_SOR; sweep++) {
-#pragma unroll
-        for (int col = 0; col < 2; col++) {
-            const int o = col ^ 1;
-            if (cact[col]) {
-#pragma unroll
-                for (int k = 0; k < SLOTS; k++) {
-                    const int idx = base + k * TY * NP;
-                    const int y = ystart + k * TY;
-                    const bool ract = (1 + ty + k * TY) <= DH - 2 && y >= 0 && y < H;
-                    if (ract) {
-                        const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
-                        float wsP = s.ws[col][idx];
-                        float sR = hasR[col] ? wsP : 0.f, sD = (y < H - 1) ? wsP : 0.f;
-                        float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = (y > 0) ? s.ws[o][iU] : 0.f;
-                        float u = s.du[col][idx], v = s.dv[col][idx];
-                        vr_sor_update(u, v, sL, sR, sU, sD, s.du[o][iL], s.du[o][iR], s.du[o][iU], s.du[o][iD], s.dv[o][iL], s.dv[o][iR],
-                                      s.dv[o][iU], s.dv[o][iD], B1[k][col], B2[k][col], A12[k][col], A11[k][col], A22[k][col]);
-                        s.du[col][idx] = u;
-                        s.dv[col][idx] = v;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    // tile + halo + derivative taps inside the image?  (uniform per CTA)
+    const bool interior = ix0 >= 0 && iy0 >= 0 && dx0 + DW + 1 <= W && dy0 + DH + 1 <= H;
+    if (interior) pair_phases<true>(s, tid, dx0, dy0, W, H);
+    else pair_phases<false>(s, tid, dx0, dy0, W, H);
 
     // ---- write the tile -----------------------------------------------------------------------------------------------
     for (int e = tid; e < OTH * OTW; e += NT) {

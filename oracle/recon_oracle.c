@@ -418,6 +418,8 @@ static void tri_ctx_init(TriCtx *c, const float *Pmain, const float *cams, int S
     }
 }
 
+/* diagnostics: if non-NULL, receives (first iteration index at which z repeats an earlier value, period) */
+static __thread int *g_cycle_out = 0;
 /* returns number of Newton iterations performed */
 static int triangulate_pixel(const TriCtx *c, float x, float y, const float *meas /*S*2*/, const float *icov /*S*4*/,
                              float depth, float *out4, float *pdf_out)
@@ -426,7 +428,14 @@ static int triangulate_pixel(const TriCtx *c, float x, float y, const float *mea
     float k[4] = {x, y, depth, 1.f};
     float p[MAX_SIDE][2], dp[MAX_SIDE][2], diff[MAX_SIDE][2];
     int iter;
+    float zhist[64];
+    int rep_at = -1, rep_period = 0;
     for (iter = 0;; iter++) {
+        if (g_cycle_out && rep_at < 0) {
+            for (int j = iter - 1; j >= 0; j--)
+                if (zhist[j] == k[2]) { rep_at = iter; rep_period = iter - j; break; }
+        }
+        zhist[iter] = k[2];
         for (int i = 0; i < S; i++) {
             float est[4];
             mul41(c->M[i], k, est);
@@ -472,6 +481,7 @@ static int triangulate_pixel(const TriCtx *c, float x, float y, const float *mea
         k[2] = (float)((double)k[2] + delta_z);
     }
     mul41(c->Pinv, k, out4);
+    if (g_cycle_out) { g_cycle_out[0] = rep_at; g_cycle_out[1] = rep_period; }
     return iter;
 }
 
@@ -531,9 +541,18 @@ static int triangulate_at(const TriCtx *c, const float *const *flows, const floa
     return 1;
 }
 
+void orc_triangulate_dense_ex(const float *const *flows, int S, const float *Pmain, const float *cams,
+                              const float *depth, const float *grad2, int W, int H,
+                              float *dense5, uint8_t *valid, int32_t *iters_out, int32_t *cycle_out /* H*W*2 or NULL */);
 void orc_triangulate_dense(const float *const *flows, int S, const float *Pmain, const float *cams,
                            const float *depth, const float *grad2, int W, int H,
                            float *dense5, uint8_t *valid, int32_t *iters_out)
+{
+    orc_triangulate_dense_ex(flows, S, Pmain, cams, depth, grad2, W, H, dense5, valid, iters_out, 0);
+}
+void orc_triangulate_dense_ex(const float *const *flows, int S, const float *Pmain, const float *cams,
+                              const float *depth, const float *grad2, int W, int H,
+                              float *dense5, uint8_t *valid, int32_t *iters_out, int32_t *cycle_out)
 {
     TriCtx c;
     tri_ctx_init(&c, Pmain, cams, S);
@@ -542,7 +561,10 @@ void orc_triangulate_dense(const float *const *flows, int S, const float *Pmain,
         for (int col = 0; col < W; col++) {
             size_t i = (size_t)row * W + col;
             int it = 0;
+            int cyc[2] = {-1, 0};
+            g_cycle_out = cycle_out ? cyc : 0;
             valid[i] = (uint8_t)triangulate_at(&c, flows, depth, grad2, W, H, row, col, dense5 + 5 * i, &it);
+            if (cycle_out) { cycle_out[2 * i] = cyc[0]; cycle_out[2 * i + 1] = cyc[1]; }
             if (iters_out) iters_out[i] = valid[i] ? it : -1;
             if (!valid[i]) for (int q = 0; q < 5; q++) dense5[5 * i + q] = 0.f;
         }

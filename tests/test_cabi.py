@@ -107,3 +107,35 @@ def test_cpp_host_mirror_matches_oracle(tmp_path):
     assert np.array_equal(ok, ~np.isnan(got).any(1))
     err = np.abs(got[ok, :3] / got[ok, 3:4] - ref[ok, :3] / ref[ok, 3:4]).max()
     assert err <= 1e-4 * sc.scale
+
+
+def test_register_jacobi_equals_opencv_jacobi():
+    """csrc/jacobi3.cuh (n = 3 specialisation held in registers, incl. the stale pivot bookkeeping)
+    against the oracle's line-by-line restatement of OpenCV's generic JacobiImpl_ and cv2.eigen."""
+    import ctypes as C
+    import cv2
+    import numpy as np
+    from oracle import native
+    lib = mr.load_library()
+    lib.mr_debug_jacobi3.argtypes = [C.c_void_p] * 3
+    rng = np.random.default_rng(0)
+    L = native.lib()
+    nbit = 0
+    for t in range(3000):
+        basis = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        sig = np.array([1.0, 10 ** rng.uniform(-3, 0), 10 ** rng.uniform(-6, 0)]) * 10 ** rng.uniform(-5, 1)
+        if t % 7 == 0:
+            sig[1] = sig[0]                      # repeated eigenvalues
+        cov = ((basis * sig) @ basis.T).astype(np.float32)
+        cov = ((cov + cov.T) * np.float32(0.5)).astype(np.float32)
+        c6 = np.array([cov[0, 0], cov[0, 1], cov[0, 2], cov[1, 1], cov[1, 2], cov[2, 2]], np.float32)
+        w, v = np.empty(3, np.float32), np.empty(9, np.float32)
+        assert lib.mr_debug_jacobi3(c6.ctypes.data, w.ctypes.data, v.ctypes.data) == 0
+        a = np.ascontiguousarray(cov.ravel().copy())
+        w2, v2 = np.empty(3, np.float32), np.empty(9, np.float32)
+        L.orc_jacobi3(a, w2, v2)
+        nbit += int(np.array_equal(w, w2) and np.array_equal(v, v2))
+        assert np.allclose(w, w2, rtol=1e-5, atol=1e-12) and np.allclose(np.abs(v), np.abs(v2), atol=2e-3)
+    assert nbit >= 2990          # bit-identical except where glibc's hypotf is not correctly rounded
+    ok, evals, evecs = cv2.eigen(cov)
+    assert np.allclose(evals.ravel(), w, rtol=1e-4, atol=1e-10)
