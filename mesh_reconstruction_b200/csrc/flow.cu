@@ -309,6 +309,83 @@ __global__ void strided_copy_kernel(const float *__restrict__ src, size_t N, flo
     if (i < N) out[i * stride + off] = src[i];
 }
 
+// Level 0 -> 1 for both 8-bit images, fused with the level-0 absolute difference (each thread also emits
+// the |a - b| of the 2x2 block of level-0 pixels it sits on).
+__global__ void __launch_bounds__(256) pyr_level0_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int w, int h,
+                                                         float *__restrict__ d0, float *__restrict__ ao, float *__restrict__ bo,
+                                                         float *__restrict__ d1, int wo, int ho)
+{
+    int X = blockIdx.x * blockDim.x + threadIdx.x;
+    int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= wo || Y >= ho) return;
+    float va = pyr_down_at(a, w, h, X, Y), vb = pyr_down_at(b, w, h, X, Y);
+    size_t o = (size_t)Y * wo + X;
+    ao[o] = va;
+    bo[o] = vb;
+    d1[o] = fabsf(va - vb);
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+            int x = 2 * X + dx, y = 2 * Y + dy;
+            if (x < w && y < h) {
+                size_t i = (size_t)y * w + x;
+                d0[i] = fabsf((float)a[i] - (float)b[i]);
+            }
+        }
+}
+
+// All small levels in ONE launch: a single CTA takes level t-1 from global memory, builds levels t .. L-1
+// (both images + differences) in shared memory, folds the differences back up (d_l += pyrUp(d_{l+1})) and
+// writes the accumulated level-t difference.  Replaces 2 x (L - t) tiny launches.
+struct TailGeom {
+    int t, L;
+    int w[MR_MAX_LEVELS], h[MR_MAX_LEVELS];
+    int off[MR_MAX_LEVELS];   // offsets inside the shared-memory planes (levels >= t)
+    int total;
+};
+
+__global__ void __launch_bounds__(1024) pyr_tail_kernel(const float *__restrict__ a_in, const float *__restrict__ b_in, TailGeom g,
+                                                        float *__restrict__ d_out)
+{
+    extern __shared__ float tail_smem[];
+    float *A = tail_smem, *B = A + g.total, *D = B + g.total;
+    for (int l = g.t; l < g.L; l++) {
+        const int w = g.w[l - 1], h = g.h[l - 1], wo = g.w[l], ho = g.h[l];
+        const float *sa = (l == g.t) ? a_in : A + g.off[l - 1];
+        const float *sb = (l == g.t) ? b_in : B + g.off[l - 1];
+        for (int i = threadIdx.x; i < wo * ho; i += blockDim.x) {
+            int X = i % wo, Y = i / wo;
+            float va = pyr_down_at(sa, w, h, X, Y), vb = pyr_down_at(sb, w, h, X, Y);
+            A[g.off[l] + i] = va;
+            B[g.off[l] + i] = vb;
+            D[g.off[l] + i] = fabsf(va - vb);
+        }
+        __syncthreads();
+    }
+    for (int l = g.L - 2; l >= g.t; l--) {
+        const int W = g.w[l], H = g.h[l], w = g.w[l + 1], h = g.h[l + 1];
+        const float *src = D + g.off[l + 1];
+        float *dst = D + g.off[l];
+        for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
+            int X = i % W, Y = i / W;
+            int Xc = min(X, 2 * w - 1), Yc = min(Y, 2 * h - 1);
+            int y = Yc >> 1, yd = min(y + 1, h - 1);
+            float r1 = pyr_up_row(src + y * w, w, Xc), r2 = pyr_up_row(src + yd * w, w, Xc), v;
+            if (Yc & 1) v = (r1 + r2) * (1.f / 16.f);
+            else {
+                int yu = (h > 1) ? (y == 0 ? 1 : y - 1) : 0;
+                float r0 = pyr_up_row(src + yu * w, w, Xc);
+                v = ((r1 * 6.f + r0) + r2) * (1.f / 64.f);
+            }
+            dst[i] = dst[i] + v;
+        }
+        __syncthreads();
+    }
+    const int n = g.w[g.t] * g.h[g.t];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d_out[i] = D[g.off[g.t] + i];
+}
+
 int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off)
 {
     int L = ctx->n_levels;
@@ -317,31 +394,63 @@ int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, flo
     float *pd = mr_buf<float>(ctx, "pyr_d", ctx->pyr_total);
     if (!pa || !pb || !pd) return mr_fail(ctx, MR_ENOMEM, "pyr", "alloc");
     dim3 b(32, 8);
-    absdiff_u8_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d_prev, d_next, ctx->N, pd);
-    MR_LAUNCH_CHECK(ctx, "absdiff_u8_kernel");
-    for (int l = 0; l + 1 < L; l++) {
+    // first level handled by the single-CTA tail kernel: needs float inputs (t >= 2) and everything in shared memory
+    int t = L;
+    TailGeom g;
+    for (int cand = 2; cand < L; cand++) {
+        int tot = 0;
+        for (int l = cand; l < L; l++) tot += ctx->lw[l] * ctx->lh[l];
+        if (ctx->lw[cand] * ctx->lh[cand] <= 2304 && (size_t)tot * 3 * sizeof(float) <= 200 * 1024) {
+            t = cand;
+            g.total = tot;
+            break;
+        }
+    }
+    if (L >= 2) {
+        pyr_level0_kernel<<<dim3(cdiv(ctx->lw[1], 32), cdiv(ctx->lh[1], 8)), b, 0, ctx->stream>>>(
+            d_prev, d_next, ctx->lw[0], ctx->lh[0], pd, pa + ctx->loff[1], pb + ctx->loff[1], pd + ctx->loff[1], ctx->lw[1], ctx->lh[1]);
+        MR_LAUNCH_CHECK(ctx, "pyr_level0_kernel");
+    } else {
+        absdiff_u8_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d_prev, d_next, ctx->N, pd);
+        MR_LAUNCH_CHECK(ctx, "absdiff_u8_kernel");
+    }
+    for (int l = 1; l + 1 < L && l + 1 < t; l++) {
         int w = ctx->lw[l], h = ctx->lh[l], wo = ctx->lw[l + 1], ho = ctx->lh[l + 1];
-        dim3 g(cdiv(wo, 32), cdiv(ho, 8));
-        if (l == 0)
-            pyr_down_pair_kernel<uint8_t><<<g, b, 0, ctx->stream>>>(d_prev, d_next, w, h, pa + ctx->loff[1], pb + ctx->loff[1],
-                                                                    pd + ctx->loff[1], wo, ho);
-        else
-            pyr_down_pair_kernel<float><<<g, b, 0, ctx->stream>>>(pa + ctx->loff[l], pb + ctx->loff[l], w, h, pa + ctx->loff[l + 1],
-                                                                  pb + ctx->loff[l + 1], pd + ctx->loff[l + 1], wo, ho);
+        pyr_down_pair_kernel<float><<<dim3(cdiv(wo, 32), cdiv(ho, 8)), b, 0, ctx->stream>>>(
+            pa + ctx->loff[l], pb + ctx->loff[l], w, h, pa + ctx->loff[l + 1], pb + ctx->loff[l + 1], pd + ctx->loff[l + 1], wo, ho);
         MR_LAUNCH_CHECK(ctx, "pyr_down_pair_kernel");
+    }
+    if (t < L) {
+        g.t = t;
+        g.L = L;
+        int off = 0;
+        for (int l = 0; l < L; l++) {
+            g.w[l] = ctx->lw[l];
+            g.h[l] = ctx->lh[l];
+            g.off[l] = 0;
+            if (l >= t) { g.off[l] = off; off += ctx->lw[l] * ctx->lh[l]; }
+        }
+        size_t smem = (size_t)g.total * 3 * sizeof(float);
+        static size_t attr_set = 0;
+        if (smem > attr_set) {
+            MR_CUDA(ctx, cudaFuncSetAttribute(pyr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = smem;
+        }
+        pyr_tail_kernel<<<1, 1024, smem, ctx->stream>>>(pa + ctx->loff[t - 1], pb + ctx->loff[t - 1], g, pd + ctx->loff[t]);
+        MR_LAUNCH_CHECK(ctx, "pyr_tail_kernel");
     }
     if (L == 1) {
         // degenerate (min(H,W) <= 2): the result is the level-0 difference
         strided_copy_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(pd, ctx->N, d_out, out_stride, out_off);
         MR_LAUNCH_CHECK(ctx, "strided_copy_kernel");
     }
-    for (int l = L - 2; l >= 0; l--) {
+    for (int l = (t < L ? t - 1 : L - 2); l >= 0; l--) {
         int W = ctx->lw[l], H = ctx->lh[l], w = ctx->lw[l + 1], h = ctx->lh[l + 1];
-        dim3 g(cdiv(W, 32), cdiv(H, 8));
+        dim3 gg(cdiv(W, 32), cdiv(H, 8));
         if (l == 0)
-            pyr_up_add_kernel<<<g, b, 0, ctx->stream>>>(pd + ctx->loff[1], w, h, pd, W, H, d_out, out_stride, out_off);
+            pyr_up_add_kernel<<<gg, b, 0, ctx->stream>>>(pd + ctx->loff[1], w, h, pd, W, H, d_out, out_stride, out_off);
         else
-            pyr_up_add_kernel<<<g, b, 0, ctx->stream>>>(pd + ctx->loff[l + 1], w, h, pd + ctx->loff[l], W, H, pd + ctx->loff[l], 1, 0);
+            pyr_up_add_kernel<<<gg, b, 0, ctx->stream>>>(pd + ctx->loff[l + 1], w, h, pd + ctx->loff[l], W, H, pd + ctx->loff[l], 1, 0);
         MR_LAUNCH_CHECK(ctx, "pyr_up_add_kernel");
     }
     return MR_OK;
