@@ -1,0 +1,163 @@
+"""GPU tests: edge cases the reference's domain has (empty / ragged / tiny inputs, S from 1 to 16,
+zero variance -> NaN rows) and size-independent properties at BASELINE.json's full sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mesh_reconstruction_b200 as mr
+from mesh_reconstruction_b200 import synth
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _oracle_main(sc, frames, fa, sides):
+    from oracle.pipeline import process_main_frame
+    from oracle.render import RenderOracle
+    ro = RenderOracle(sc.width, sc.height)
+    ro.loadMesh(sc.vertices, sc.faces)
+    return process_main_frame(ro, frames, sc.cameras, fa, sides, keep=True)
+
+
+def _assert_rows(got, ref, scale, what):
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    ng, nr = np.isnan(got).any(1), np.isnan(ref).any(1)
+    assert np.array_equal(ng, nr), what
+    ok = ~nr
+    if ok.any():
+        err = np.abs(got[ok, :3].astype(np.float64) / got[ok, 3:4] - ref[ok, :3].astype(np.float64) / ref[ok, 3:4]).max()
+        assert err <= 1e-4 * scale, (what, err)
+
+
+@pytest.mark.parametrize("W,H", [(16, 12), (33, 21), (7, 5), (64, 3)])
+def test_tiny_and_ragged_sizes(W, H):
+    sc = synth.make_scene(W, H, 3, step=0.2, mesh_err=0.03, mesh_res=3)
+    frames = sc.frames()
+    ref, inter = _oracle_main(sc, frames, 1, [0, 2])
+    r = mr.Render(W, H, ctx=mr.api.Context(W, H))
+    r.loadMesh(sc.vertices, sc.faces)
+    got = mr.process_main_frame(r, frames[1], sc.cameras[1], [frames[0], frames[2]], [sc.cameras[0], sc.cameras[2]])
+    _assert_rows(got, ref, sc.scale, f"{W}x{H}")
+    fl = mr.calculateFlow(frames[1], inter["mixed"][0])
+    assert np.array_equal(fl[..., :2], inter["flows"][0][..., :2])
+    assert np.allclose(fl[..., 2], inter["flows"][0][..., 2], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("S", [3, 5, 16])
+def test_many_side_cameras(S):
+    """S = 3, 5 use the generic kernel instantiation; 16 = MR_MAX_SIDE."""
+    W, H = 96, 72
+    n = S + 1
+    sc = synth.make_scene(W, H, n, step=0.08, mesh_err=0.03, mesh_res=6, seed=S)
+    frames = sc.frames()
+    fa = n // 2
+    sides = [i for i in range(n) if i != fa]
+    ref, _ = _oracle_main(sc, frames, fa, sides)
+    r = mr.spawnRender(W, H)
+    r.loadMesh(sc.vertices, sc.faces)
+    got = mr.process_main_frame(r, frames[fa], sc.cameras[fa], [frames[s] for s in sides], [sc.cameras[s] for s in sides])
+    _assert_rows(got, ref, sc.scale, f"S={S}")
+    with pytest.raises(mr.MeshReconError):
+        mr.process_main_frame(r, frames[fa], sc.cameras[fa], [frames[0]] * 17, [sc.cameras[0]] * 17)
+
+
+def test_empty_mesh_and_all_background():
+    W, H = 64, 48
+    sc = synth.make_scene(W, H, 2, mesh_res=3)
+    frames = sc.frames()
+    r = mr.Render(W, H, ctx=mr.api.Context(W, H))
+    r.loadMesh(np.zeros((0, 4), f32), np.zeros((0, 3), np.int32))
+    got = mr.process_main_frame(r, frames[0], sc.cameras[0], [frames[1]], [sc.cameras[1]])
+    assert got.shape == (0, 7)
+    # mesh entirely behind the camera: still everything background
+    r.loadMesh(np.array([[0, 0, 50, 1], [1, 0, 50, 1], [0, 1, 50, 1]], f32), np.array([[0, 1, 2]], np.int32))
+    assert (r.depth(sc.cameras[0]) == 1.0).all()
+    proj = r.projected(sc.cameras[0], frames[1], sc.cameras[1])
+    assert not proj.any()
+    d = np.ones((H, W), f32)
+    mixed = mr.mixBackground(proj, frames[0], d)
+    assert np.array_equal(mixed, frames[0]) and (d == 1.0).all()
+
+
+def test_zero_variance_gives_the_references_nan_rows():
+    """Quirk C11: a prediction identical to the main frame has variance 0 at level 0 ... the pyramid
+    terms keep it positive except for constant images; with a constant image everything is 0 and
+    1/variance = inf propagates to NaN rows exactly like the reference's IEEE arithmetic."""
+    from oracle.tri import triangulate_pixels
+    W, H = 48, 40
+    sc = synth.make_scene(W, H, 2, step=0.2, mesh_res=4)
+    r = mr.spawnRender(W, H)
+    r.loadMesh(sc.vertices, sc.faces)
+    depth = r.depth(sc.cameras[0])
+    flow = np.zeros((H, W, 4), f32)        # variance exactly 0
+    ref = triangulate_pixels([flow], sc.cameras[0], [sc.cameras[1]], depth)
+    got = mr.triangulatePixels([flow], sc.cameras[0], [sc.cameras[1]], depth)
+    assert got.shape == ref.shape and np.isnan(ref).any()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    flow[..., 2] = 1.0
+    flow[5:9, 7:11, 2] = 0.0                # a few zero-variance pixels among good ones
+    ref = triangulate_pixels([flow], sc.cameras[0], [sc.cameras[1]], depth)
+    got = mr.triangulatePixels([flow], sc.cameras[0], [sc.cameras[1]], depth)
+    assert np.array_equal(np.isnan(got[:, :5]), np.isnan(ref[:, :5]))
+    _assert_rows(got, ref, sc.scale, "mixed nan")
+
+
+def test_argument_errors():
+    lib = mr.load_library()
+    ctx = mr.api.Context(32, 24)
+    assert lib.mr_depth(ctx.h, None, None) == -1
+    assert lib.mr_calculate_flow(ctx.h, None, None, 0, None) == -1
+    assert b"null" in lib.mr_last_error(ctx.h)
+    assert lib.mr_load_mesh(ctx.h, None, -1, None, 0) == -1
+    h = C.c_void_p()
+    assert lib.mr_create(C.byref(h), 0, 0, 10) == -1
+    assert lib.mr_create(C.byref(h), 99, 10, 10) == -2
+
+
+def _pixel_of_rows(rows, P, W, H):
+    X = rows[:, :4].astype(np.float64)
+    k = (P.astype(np.float64) @ X.T).T
+    k = k[:, :3] / k[:, 3:4]
+    col = k[:, 0] * W / 2 + W / 2
+    row = H / 2 - k[:, 1] * H / 2
+    return row, col
+
+
+@pytest.mark.parametrize("W,H,S,with_oracle", [(1920, 1080, 1, True), (3840, 2160, 4, False)])
+def test_full_size_properties(W, H, S, with_oracle):
+    """BASELINE configs 4 (1080p, S=1) and 5 (4K, S=4) at full size.  Properties: determinism; the fused
+    call equals the sequence of individual entry points bit for bit; rows come out in row-major pixel
+    order, one per surviving pixel; at 1080p additionally the full oracle comparison."""
+    n = S + 1
+    sc = synth.make_scene(W, H, 300, step=0.006, mesh_err=0.02)
+    fa = 150
+    sides = ([fa + 1] if S == 1 else [fa - 2, fa - 1, fa + 1, fa + 2])
+    frames = {i: sc.frame(i) for i in [fa] + sides}
+    r = mr.Render(W, H, ctx=mr.api.Context(W, H))
+    r.loadMesh(sc.vertices, sc.faces)
+    args = (frames[fa], sc.cameras[fa], [frames[s] for s in sides], [sc.cameras[s] for s in sides])
+    a = mr.process_main_frame(r, *args).copy()
+    b = mr.process_main_frame(r, *args).copy()
+    assert np.array_equal(a, b, equal_nan=True)                         # deterministic
+    # individual entry points, in the reference's order (recon.cpp:70-114)
+    depth = r.depth(sc.cameras[fa])
+    flows = []
+    for s in sides:
+        proj = r.projected(sc.cameras[fa], frames[s], sc.cameras[s])
+        mixed = mr.mixBackground(proj, frames[fa], depth)
+        flows.append(mr.calculateFlow(frames[fa], mixed))
+    c = mr.triangulatePixels(flows, sc.cameras[fa], [sc.cameras[s] for s in sides], depth)
+    assert np.array_equal(a, c, equal_nan=True)                         # fused == unfused, bit for bit
+    # one row per surviving pixel, in row-major order, and the point reprojects onto its own pixel
+    ok = np.isfinite(a).all(1)
+    row, col = _pixel_of_rows(a[ok], sc.cameras[fa], W, H)
+    lin = np.rint(row) * W + np.rint(col)
+    assert np.abs(row - np.rint(row)).max() < 0.02 and np.abs(col - np.rint(col)).max() < 0.02
+    assert (np.diff(lin) > 0).all()
+    assert len(a) <= int((depth != 1.0).sum()) and len(a) > 0.9 * W * H
+    assert not flows[0][..., 3].any() and np.isfinite(flows[0]).all()
+    if with_oracle:
+        ref, inter = _oracle_main(sc, frames, fa, sides)
+        assert np.array_equal(flows[0][..., :2], inter["flows"][0][..., :2])
+        _assert_rows(a, ref, sc.scale, "1080p vs oracle")
