@@ -288,6 +288,13 @@ def main():
     ach = dom_bytes_launch / (dom_ms_launch * 1e-3) / 1e9
     path_ach = ALG_BYTES_PATH(1) * N * B * K * 1.0 / (ms_res * 1e-3) / 1e9     # per GPU
 
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if (W, H) == (1920, 1080) and dom in tj and tj[dom].get("dram_bytes_per_launch"):
+            traffic = tj[dom]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     pix_total = world * B * K * N
     value = pix_total / (ms_res * 1e-3) / 1e6
     e2e_val = pix_total / (ms_e2e * 1e-3) / 1e6
@@ -318,7 +325,8 @@ def main():
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_pixel": STAGE_ALG_BYTES[dom],
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "compute-bound stage (IEEE-exact div/sqrt, FP64 islands): HBM fraction is low by construction, see DESIGN.md section 4", "alg_bytes_per_pixel": STAGE_ALG_BYTES[dom],
                          "ms_per_launch": dom_ms_launch, "launches_per_pair": stages[dom]["launches_per_pair"]},
             "roofline_path": {"alg_bytes_per_pixel_pair": ALG_BYTES_PATH(1), "achieved": path_ach, "peak": peak, "unit": "GB/s",
                               "frac": path_ach / peak},

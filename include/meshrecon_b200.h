@@ -64,6 +64,14 @@ int mr_synchronize(mr_context *ctx);
 int mr_load_mesh(mr_context *ctx, const float *vertices_xyzw, int n_vertices, const int32_t *faces, int n_faces);
 /* Render::depth  render_glx.cpp:369-397.  out: H*W float32 NDC z. */
 int mr_depth(mr_context *ctx, const float camera[16], float *out_depth);
+/* Batched single-pixel depth queries for Heuristic::chooseCameras / filterCameras (heuristic.cpp:285-341,
+ * 456): for each of n_cameras "viewer" matrices (n_cameras*16 floats) the scene is rasterised on the device
+ * and only out[i*n + j] = depth.at<float>(rows[i*n + j], cols[i*n + j]) is returned (rows/cols: n_cameras *
+ * n_per_camera int32).  Same values as mr_depth() followed by host indexing; rows outside [0,H) or cols
+ * outside [0,W] give MR_BACKGROUND_DEPTH, col == W reads the next row's first pixel like the reference's
+ * continuous cv::Mat does. */
+int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const int32_t *rows, const int32_t *cols,
+                     int n_per_camera, float *out);
 /* Render::projected  render_glx.cpp:261-367 + shader.vert:9-13 + shader.frag:11-25.
  * frame: H*W uint8 (side camera's gray frame); out_rgb: H*W*3 uint8 (R = predicted gray,
  * G = B = 255 where visible and in-frame, else 0,0,0). */

@@ -56,6 +56,7 @@ def load_library():
     L.mr_load_mesh.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.mr_depth.argtypes = [vp, vp, vp]
     L.mr_projected.argtypes = [vp, vp, vp, vp, vp]
+    L.mr_depth_samples.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
     L.mr_mix_background.argtypes = [vp, vp, vp, vp, vp]
     L.mr_calculate_flow.argtypes = [vp, vp, vp, C.c_int, vp]
     L.mr_flow_remap.argtypes = [vp, vp, C.c_int, vp, vp]
@@ -180,6 +181,18 @@ class Render:
             out = np.empty((self.H, self.W), np.float32)
         po, _ = _ptr(out, np.float32)
         self.ctx.check(self.ctx.lib.mr_depth(self.ctx.h, pc, po))
+        return out
+
+    def depthSamples(self, cameras, rows, cols):
+        """Batched ``depth(viewer).at<float>(row, col)`` queries (heuristic.cpp:306-311,456): ``cameras`` is
+        m x 4 x 4, ``rows`` / ``cols`` are m x n int32; returns m x n float32 without reading back depth maps."""
+        cams = np.ascontiguousarray(np.asarray(cameras, np.float32).reshape(-1, 16))
+        rows = np.ascontiguousarray(np.asarray(rows, np.int32).reshape(len(cams), -1))
+        cols = np.ascontiguousarray(np.asarray(cols, np.int32).reshape(len(cams), -1))
+        assert rows.shape == cols.shape
+        out = np.empty(rows.shape, np.float32)
+        self.ctx.check(self.ctx.lib.mr_depth_samples(self.ctx.h, cams.ctypes.data, len(cams), rows.ctypes.data, cols.ctypes.data,
+                                                     rows.shape[1], out.ctypes.data))
         return out
 
     def projected(self, camera, frame, projector, out=None):

@@ -217,6 +217,34 @@ int mr_depth(mr_context *ctx, const float camera[16], float *out_depth)
     return MR_OK;
 }
 
+int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const int32_t *rows, const int32_t *cols, int n_per_camera,
+                     float *out)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, cameras && rows && cols && out, "null argument");
+    CHECK_ARG(ctx, n_cameras >= 0 && n_per_camera >= 0, "negative count");
+    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_depth_samples", "loadMesh has not been called");
+    size_t total = (size_t)n_cameras * n_per_camera;
+    if (total == 0) return MR_OK;
+    unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
+    const int32_t *d_rows = (const int32_t *)mr_in(ctx, rows, total * sizeof(int32_t), "q_rows");
+    const int32_t *d_cols = (const int32_t *)mr_in(ctx, cols, total * sizeof(int32_t), "q_cols");
+    bool dev_out = mr_is_device_ptr(out);
+    float *d_out = dev_out ? out : mr_buf<float>(ctx, "q_out", total);
+    if (!vis || !d_rows || !d_cols || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_depth_samples", "alloc");
+    for (int i = 0; i < n_cameras; i++) {      // all shots are enqueued back to back; one read-back at the end
+        RC(k_raster(ctx, to_mat4(cameras + 16 * i), vis));
+        RC(k_depth_samples(ctx, vis, d_rows + (size_t)i * n_per_camera, d_cols + (size_t)i * n_per_camera, n_per_camera,
+                           d_out + (size_t)i * n_per_camera));
+    }
+    if (!dev_out) {
+        RC(mr_out(ctx, out, d_out, total * sizeof(float)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
 // shadow pass + dilation for `projector`, leaves the dilated map in "shadow_dil"
 static int shadow_pass(mr_context *ctx, const float *projector, float **out)
 {

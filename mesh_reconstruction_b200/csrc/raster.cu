@@ -397,3 +397,35 @@ int k_mix_background(mr_context *ctx, const uint8_t *d_rgb, const uint8_t *d_bg,
     MR_LAUNCH_CHECK(ctx, "mix_background_kernel");
     return MR_OK;
 }
+
+// ---- single-pixel depth queries (heuristic.cpp:285-341,456) ------------------------------------------------
+// Heuristic::chooseCameras renders a full depth map from a synthetic "viewer" camera for each of its 200
+// surface shots and then reads ONE pixel per candidate camera (filterCameras, heuristic.cpp:306-311).
+// The queries are answered on the device straight from the visibility buffer, so only n floats per shot
+// cross PCIe instead of a W x H map.  Addressing follows the reference's depth.at<float>(row, col) on a
+// continuous Mat (its `col > depth.cols` test lets col == W through, which reads the next row's first
+// pixel); rows outside [0, H) or cols outside [0, W] give the background depth.
+__global__ void depth_samples_kernel(const unsigned long long *__restrict__ vis, int W, int H, const int32_t *__restrict__ rows,
+                                     const int32_t *__restrict__ cols, int n, float *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = rows[i], c = cols[i];
+    float d = MR_BACKGROUND_DEPTH;
+    if (r >= 0 && r < H && c >= 0 && c <= W) {
+        long long idx = (long long)r * W + c;
+        long long last = (long long)W * H - 1;
+        if (idx > last) idx = last;
+        unsigned long long k = vis[idx];
+        if (k != BG_KEY) d = ord_to_z((unsigned int)(k >> 32));
+    }
+    out[i] = d;
+}
+
+int k_depth_samples(mr_context *ctx, const unsigned long long *d_vis, const int32_t *d_rows, const int32_t *d_cols, int n, float *d_out)
+{
+    if (n <= 0) return MR_OK;
+    depth_samples_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(d_vis, ctx->W, ctx->H, d_rows, d_cols, n, d_out);
+    MR_LAUNCH_CHECK(ctx, "depth_samples_kernel");
+    return MR_OK;
+}

@@ -161,3 +161,39 @@ def test_full_size_properties(W, H, S, with_oracle):
         ref, inter = _oracle_main(sc, frames, fa, sides)
         assert np.array_equal(flows[0][..., :2], inter["flows"][0][..., :2])
         _assert_rows(a, ref, sc.scale, "1080p vs oracle")
+
+
+def test_depth_samples_match_full_depth_maps():
+    """chooseCameras' visibility shots (heuristic.cpp:456 + 306-311) as batched
+    single-pixel queries -- identical to indexing the full depth map of each viewer."""
+    import time
+    from oracle.render import RenderOracle
+    W, H = 640, 480
+    sc = synth.make_scene(W, H, 40, step=0.05, mesh_res=16)
+    r = mr.spawnRender(W, H)
+    r.loadMesh(sc.vertices, sc.faces)
+    ro = RenderOracle(W, H)
+    ro.loadMesh(sc.vertices, sc.faces)
+    rng = np.random.default_rng(0)
+    m, n = 40, 173
+    rows = rng.integers(-3, H + 3, (m, n)).astype(np.int32)
+    cols = rng.integers(-3, W + 3, (m, n)).astype(np.int32)
+    cols[0, :5] = W                                    # the reference's off-by-one column
+    rows[0, :5] = [0, 5, H - 2, H - 1, 7]
+    t0 = time.perf_counter()
+    got = r.depthSamples(sc.cameras[:m], rows, cols)
+    t_batched = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    maps = [r.depth(sc.cameras[i]) for i in range(m)]
+    t_full = time.perf_counter() - t0
+    for i in range(m):
+        d = maps[i]
+        if i < 3:
+            assert np.array_equal(d, ro.depth(sc.cameras[i]))
+        flat = d.ravel()
+        exp = np.full(n, 1.0, f32)
+        ok = (rows[i] >= 0) & (rows[i] < H) & (cols[i] >= 0) & (cols[i] <= W)
+        idx = np.minimum(rows[i].astype(np.int64) * W + cols[i], W * H - 1)
+        exp[ok] = flat[idx[ok]]
+        assert np.array_equal(got[i], exp)
+    print(f"depth shots: batched {1e3 * t_batched:.2f} ms vs {1e3 * t_full:.2f} ms for {m} full read-backs")
