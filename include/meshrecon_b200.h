@@ -83,8 +83,8 @@ int mr_projected(mr_context *ctx, const float camera[16], const uint8_t *frame, 
 int mr_mix_background(mr_context *ctx, const uint8_t *image_rgb, const uint8_t *background, float *depth_inout,
                       uint8_t *out_mixed);
 /* calculateFlow  flow.cpp:19-42.  out: H*W*4 float32 (u, v, variance, 0).
- * use_farneback != 0 selects the reference's -f branch, which is NOT implemented in this
- * round: the call then fails with MR_EINVAL, it never falls back. */
+ * use_farneback == 0: cv::optflow VariationalRefinement (flow.cpp:29, the reference's default);
+ * use_farneback != 0: cv::FarnebackOpticalFlow with the reference's parameters (flow.cpp:22-26). */
 int mr_calculate_flow(mr_context *ctx, const uint8_t *prev, const uint8_t *next, int use_farneback, float *out_flow4);
 /* flowRemap  util.cpp:390-403.  flow: H*W*stride_floats float32 with (u, v) first
  * (stride_floats = 2 for CV_32FC2 or 4 for the flow record); out: H*W uint8. */
@@ -112,6 +112,9 @@ int mr_extract_camera_center(const float camera[16], float out_center3[3]);
 int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                           const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
                           int *out_count);
+/* The reference's `-f` switch (Configuration::useFarneback, configuration.cpp:26,92) for
+ * mr_process_main_frame[_async]; off by default like the reference. */
+int mr_set_use_farneback(mr_context *ctx, int on);
 /* Pipelined variant for HOST (ideally pinned) out_points: returns as soon as the rows are complete on
  * the device and *out_count is known; their device->host copy into out_points runs on a second
  * stream and overlaps the NEXT call's compute (two internal row buffers are ping-ponged).  The caller

@@ -78,6 +78,7 @@ def load_library():
     L.mr_launch_count.argtypes = [vp]
     L.mr_launch_count.restype = C.c_uint64
     L.mr_set_vr_impl.argtypes = [C.c_int]
+    L.mr_set_use_farneback.argtypes = [vp, C.c_int]
     L.mr_profile_enable.argtypes = [vp, C.c_int]
     L.mr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.mr_stage_name.argtypes = [C.c_int]

@@ -174,6 +174,14 @@ int mr_wait_copies(mr_context *ctx)
     return MR_OK;
 }
 
+// Configuration::useFarneback (configuration.cpp:26, -f) for the fused main-frame call
+int mr_set_use_farneback(mr_context *ctx, int on)
+{
+    CHECK_CTX(ctx);
+    ctx->use_farneback = on != 0;
+    return MR_OK;
+}
+
 // debug / benchmarking knob: 0 = plane-per-stage VR kernels, 1 = fused tile kernel with TMA staging
 // (default), 2 = fused tile kernel with plain loads
 int mr_set_vr_impl(int impl)
@@ -303,13 +311,14 @@ int mr_mix_background(mr_context *ctx, const uint8_t *image_rgb, const uint8_t *
 }
 
 // device-side calculateFlow: VR -> remap -> compare -> pack (flow.cpp:29-40)
-static int calculate_flow_dev(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4)
+static int calculate_flow_dev(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4, bool farneback)
 {
     uint8_t *remapped = mr_buf<uint8_t>(ctx, "remapped", ctx->N);
     if (!remapped) return mr_fail(ctx, MR_ENOMEM, "calculate_flow", "alloc");
     {
         StageScope sc(ctx, ST_VR);
-        RC(k_variational_refinement(ctx, d_prev, d_next, d_flow4));  // writes (u, v, 0, 0)
+        if (farneback) RC(k_farneback(ctx, d_prev, d_next, d_flow4));                // flow.cpp:22-26
+        else RC(k_variational_refinement(ctx, d_prev, d_next, d_flow4));               // flow.cpp:29; both write (u, v, 0, 0)
     }
     {
         StageScope sc(ctx, ST_REMAP);
@@ -327,13 +336,12 @@ int mr_calculate_flow(mr_context *ctx, const uint8_t *prev, const uint8_t *next,
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
     CHECK_ARG(ctx, prev && next && out_flow4, "null argument");
-    CHECK_ARG(ctx, !use_farneback, "Farneback branch (flow.cpp:22-26) is not implemented; no fallback is taken");
     const uint8_t *d_prev = (const uint8_t *)mr_in(ctx, prev, ctx->N, "in_main");
     const uint8_t *d_next = (const uint8_t *)mr_in(ctx, next, ctx->N, "in_side");
     bool dev_out = mr_is_device_ptr(out_flow4);
     float *d_flow = dev_out ? out_flow4 : mr_buf<float>(ctx, "flow0", ctx->N * 4);
     if (!d_prev || !d_next || !d_flow) return mr_fail(ctx, MR_ENOMEM, "mr_calculate_flow", "alloc");
-    RC(calculate_flow_dev(ctx, d_prev, d_next, d_flow));
+    RC(calculate_flow_dev(ctx, d_prev, d_next, d_flow, use_farneback != 0));
     if (!dev_out) {
         RC(mr_out(ctx, out_flow4, d_flow, ctx->N * 4 * sizeof(float)));
         MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -475,7 +483,7 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
             RC(k_shade(ctx, vis_main, Pm, to_mat4(side_cameras + 16 * i), d_side, shd, nullptr, d_main, depth,
                        mixed));                                                  // recon.cpp:85-86
         }
-        RC(calculate_flow_dev(ctx, d_main, mixed, flow));                        // recon.cpp:89
+        RC(calculate_flow_dev(ctx, d_main, mixed, flow, ctx->use_farneback));                        // recon.cpp:89
         d_flows[i] = flow;
     }
     bool dev_out = out_points && mr_is_device_ptr(out_points);

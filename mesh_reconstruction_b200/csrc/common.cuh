@@ -55,6 +55,7 @@ struct mr_context {
     std::map<std::string, DevBuf> bufs;
     // mesh (Render::loadMesh)
     int F = 0;
+    bool use_farneback = false;   // mr_set_use_farneback: the reference's -f switch for mr_process_main_frame
     // last results
     int last_count = 0;
     int last_S = 0;
@@ -155,6 +156,7 @@ int k_mix_background(mr_context *ctx, const uint8_t *d_rgb, const uint8_t *d_bg,
 int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4);
 int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const uint8_t *d_img, uint8_t *d_out);
 int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off);
+int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4);   // farneback.cu
 int k_zero_channel(mr_context *ctx, float *d_flow4, int channel);
 int mr_flow_init_tables(mr_context *ctx);
 // tri.cu

@@ -149,3 +149,19 @@ def test_float_reciprocal_equals_double_rounded_reciprocal():
     s2 = (rng.integers(0x00800000, 0x7F000000, 1 << 20, dtype=np.uint32)).view(np.float32)
     with np.errstate(all="ignore"):
         assert np.array_equal((1.0 / s2.astype(np.float64)).astype(np.float32), np.float32(1.0) / s2)
+
+
+def test_farneback_restatement_matches_cv2():
+    """oracle/farneback_np.py (the formulas csrc/farneback.cu is written from) vs the cv2 binary."""
+    from oracle import farneback_np as fb
+    rng = np.random.default_rng(0)
+    H, W = 96, 128
+    base = cv2.resize(rng.normal(128, 45, (H // 8 + 3, W // 8 + 3)).astype(f32), (W + 16, H + 16), interpolation=cv2.INTER_CUBIC)
+    p = np.clip(base[8:8 + H, 8:8 + W], 0, 255).astype(np.uint8)
+    M = np.float32([[1, 0, 1.3], [0, 1, -0.7]])
+    n = np.clip(cv2.warpAffine(base, M, (W + 16, H + 16), flags=cv2.INTER_CUBIC)[8:8 + H, 8:8 + W], 0, 255).astype(np.uint8)
+    ps = (H + W) / 1000.0
+    ref = cv2.FarnebackOpticalFlow_create(10, 0.8, False, (H + W) // 100, 7, 5 if ps < 1.5 else 7, ps, 0).calc(p, n, None)
+    mine = fb.farneback(p, n)
+    assert np.abs(ref - mine).max() < 1e-4
+    assert abs(np.median(ref[..., 0]) - 1.3) < 0.1 and abs(np.median(ref[..., 1]) + 0.7) < 0.1
