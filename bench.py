@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in bits.items() if self.reasons & b], "samples": len(sm)}
 
 
-def cpu_reference_pairs(scene, frames, pairs, threads):
+def cpu_reference_pairs(scene, frames, pairs, threads, farneback=False):
     """Times the CPU oracle (reference arithmetic) on the given (main, side) index pairs."""
     import cv2
     from oracle.pipeline import process_main_frame
@@ -91,7 +91,7 @@ def cpu_reference_pairs(scene, frames, pairs, threads):
     t0 = time.perf_counter()
     pts = 0
     for fa, fb in pairs:
-        tri = process_main_frame(r, frames, scene.cameras, fa, [fb])
+        tri = process_main_frame(r, frames, scene.cameras, fa, [fb], use_farneback=farneback)
         pts += len(tri)
     return time.perf_counter() - t0, pts
 
@@ -110,10 +110,10 @@ def run_reference(args):
     frames = {i: scene.frame(i) for i in range(4)}
     pairs_cycle = [(0, 1), (1, 2), (2, 3)]
     if args.warmup > 0:      # one real warm-up pair is enough (each pair is seconds of CPU work)
-        cpu_reference_pairs(scene, frames, [pairs_cycle[0]], cores)
+        cpu_reference_pairs(scene, frames, [pairs_cycle[0]], cores, args.farneback)
     t_total = 0.0
     for k in range(args.steps):
-        t, _ = cpu_reference_pairs(scene, frames, [pairs_cycle[k % 3]], cores)
+        t, _ = cpu_reference_pairs(scene, frames, [pairs_cycle[k % 3]], cores, args.farneback)
         t_total += t
     pix = args.steps * W * H
     val = pix / t_total / 1e6
@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--mesh-err", type=float, default=0.02)
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame pairs timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--vr-impl", type=int, default=None)
+    ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,6 +182,8 @@ def main():
     render = mr.Render(W, H, ctx=mr.api.Context(W, H, local))
     ctx = render.ctx
     render.loadMesh(scene.vertices, scene.faces)
+    if args.farneback:
+        lib.mr_set_use_farneback(ctx.h, 1)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     nbuf = 2 if world > 1 else 1
@@ -307,7 +310,7 @@ def main():
         sc4 = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err)
         sc4.cameras = cams[idx[0]:idx[0] + len(fr)]
         prs = [(i, i + 1) for i in range(len(fr) - 1)]
-        t, _ = cpu_reference_pairs(sc4, fr, prs, cores)
+        t, _ = cpu_reference_pairs(sc4, fr, prs, cores, args.farneback)
         import cv2
         cpu = {"value": len(prs) * N / t / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
                "sample": f"{len(prs)} frame pairs of {W}x{H} (of the 299-pair workload), cv2 {cv2.__version__} x{cores} threads + C restatement (OpenMP)"}
@@ -318,7 +321,7 @@ def main():
             "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S=1 (BASELINE config 4)",
-                       "pairs_per_step_per_gpu": B, "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
+                       "pairs_per_step_per_gpu": B, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
                        "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
                        "exchange": "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step" if world > 1 else "none (single GPU)"},
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": int(m_mean * 28 * B),

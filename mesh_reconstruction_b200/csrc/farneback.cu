@@ -184,15 +184,20 @@ __global__ void __launch_bounds__(256) fb_update_matrices_kernel(const float *__
 }
 
 // FarnebackUpdateFlow_Blur, vertical part: box sums over rows y-m .. y+m (rows clamped) in double,
-// one thread per (column, channel) sliding down the image like OpenCV's vsum.
+// one thread per (column, channel, 32-row segment) sliding down its segment like OpenCV's vsum.
+#define FB_VSEG 32
 __global__ void __launch_bounds__(128) fb_box_v_kernel(const float *__restrict__ M, int W, int H, int m, double *__restrict__ vs)
 {
     int xc = blockIdx.x * blockDim.x + threadIdx.x;   // x*5 + c
     if (xc >= W * 5) return;
     const size_t st = (size_t)W * 5;
-    double s = (double)M[xc] * (double)(m + 2);                                            // rows -m-1 .. 0 -> (m+2) copies of row 0
-    for (int y = 1; y < m; y++) s += (double)M[(size_t)min(y, H - 1) * st + xc];
-    for (int y = 0; y < H; y++) {
+    const int y0 = blockIdx.y * FB_VSEG, y1 = min(y0 + FB_VSEG, H);
+    // window of row y0: rows y0-m .. y0+m, clamped (for y0 = 0 this is OpenCV's (m+2)*row0 + ... initialisation
+    // followed by its first slide); then one add and one subtract per row like OpenCV's vsum
+    double s = 0;
+    for (int j = -m; j <= m; j++) s += (double)M[(size_t)min(max(y0 + j, 0), H - 1) * st + xc];
+    vs[(size_t)y0 * st + xc] = s;
+    for (int y = y0 + 1; y < y1; y++) {
         s += (double)M[(size_t)min(y + m, H - 1) * st + xc] - (double)M[(size_t)max(y - m - 1, 0) * st + xc];
         vs[(size_t)y * st + xc] = s;
     }
@@ -364,7 +369,7 @@ int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, f
         MR_LAUNCH_CHECK(ctx, "fb_update_matrices_kernel");
         const int m = winsize / 2;
         for (int it = 0; it < iterations; it++) {
-            fb_box_v_kernel<<<cdiv(w * 5, 128), 128, 0, ctx->stream>>>(M, w, h, m, vs);
+            fb_box_v_kernel<<<dim3(cdiv(w * 5, 128), cdiv(h, FB_VSEG)), 128, 0, ctx->stream>>>(M, w, h, m, vs);
             MR_LAUNCH_CHECK(ctx, "fb_box_v_kernel");
             fb_box_h_solve_kernel<<<dim3(cdiv(w, FB_SEG), h), FB_SEG, (FB_SEG + 2 * m) * 5 * sizeof(double), ctx->stream>>>(vs, w, h, m, winsize, flow);
             MR_LAUNCH_CHECK(ctx, "fb_box_h_solve_kernel");
