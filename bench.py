@@ -188,11 +188,13 @@ def main():
 
     nbuf = 2 if world > 1 else 1
     rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
-    rows_pin = [torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
+    rows_pin = [torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(B)]   # every pair of a step lands on the host
+    counts_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
     counts = torch.zeros(B, dtype=torch.int64)
     rows_flat = [r.view(B * N, 7) for r in rows_dev]
     gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
-    gather_counts = [torch.empty((world * B,), dtype=torch.int64, device=dev) for _ in range(nbuf)] if world > 1 else None
+    gather_counts = [torch.empty((world * B,), dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    counts_dev = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(nbuf)]
     pending = [None] * nbuf
 
     def pair(j):                      # j-th pair of this rank, cycling inside its block
@@ -208,33 +210,31 @@ def main():
             pending[k] = None
 
     def step_resident(s):
+        # fully asynchronous: mr_submit_main_frame never waits for the GPU, the host queues pairs (and steps) back to back.
+        # The normals kernel writes each pair's rows straight into the all-gather send buffer (slot b of the step).
         k = s % nbuf
         wait_pending(k)
-        off = 0
         for b in range(B):
             a, c = pair(s * B + b)
-            # the normals kernel writes the rows straight into the all-gather send buffer at this rank's running offset
-            m = mr.process_main_frame(render, frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
-                                      out=rows_flat[k][off:], want_host=False)
-            counts[b] = m
-            off += m
+            mr.submit_main_frame(render, frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
+                                 out=rows_dev[k][b], out_count=counts_dev[k][b:b + 1])
         if world > 1:
-            # the path's one exchange step: point rows + counts -> every rank, over NCCL/NVLink, ASYNC so that it
-            # overlaps the next step's compute (double-buffered send/receive buffers; rows are complete: the call above synced)
-            h1 = dist.all_gather_into_tensor(gather_counts[k], counts.to(dev, non_blocking=False), async_op=True)
+            # the path's one exchange step: point rows + counts -> every rank over NCCL/NVLink, ASYNC so that it
+            # overlaps the next step's compute (double-buffered send/receive buffers, stream-ordered after this step's kernels)
+            torch.cuda.current_stream().wait_stream(lib_stream)
+            h1 = dist.all_gather_into_tensor(gather_counts[k], counts_dev[k], async_op=True)
             h2 = dist.all_gather_into_tensor(gather_rows[k], rows_flat[k], async_op=True)
             pending[k] = (h1, h2)
 
     def step_e2e(s):
-        # host frames in (pinned, H2D inside the call), point rows out to pinned host memory every pair; the D2H
-        # of pair b overlaps the compute of pair b+1 (mr_process_main_frame_async, two host buffers)
-        tot = 0
+        # host frames in (pinned; H2D inside the call), every pair's point rows + count out to pinned host memory by the
+        # library's device-side copy (overlapping the next pairs' compute); the step ends when all B results are on the host
         for b in range(B):
             a, c = pair(s * B + b)
-            tot += mr.process_main_frame(render, frames_pin[a].numpy(), cams[idx[a]], [frames_pin[c].numpy()], [cams[idx[c]]],
-                                         out=rows_pin[b & 1].numpy(), want_host=True, async_copy=True)
-        ctx.wait_copies()
-        return tot
+            mr.submit_main_frame(render, frames_pin[a], cams[idx[a]], [frames_pin[c]], [cams[idx[c]]],
+                                 out=rows_pin[b], out_count=counts_pin[b:b + 1])
+        ctx.synchronize()
+        return int(counts_pin.sum())
 
     def barrier():
         torch.cuda.synchronize()
@@ -301,7 +301,7 @@ def main():
     pix_total = world * B * K * N
     value = pix_total / (ms_res * 1e-3) / 1e6
     e2e_val = pix_total / (ms_e2e * 1e-3) / 1e6
-    m_mean = float(counts.float().mean())
+    m_mean = float(counts_dev[(Wm + K - 1) % nbuf].float().mean())
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_pairs > 0:
@@ -324,7 +324,7 @@ def main():
                        "pairs_per_step_per_gpu": B, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
                        "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
                        "exchange": "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step" if world > 1 else "none (single GPU)"},
-            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": int(m_mean * 28 * B),
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": int(m_mean * 28 * B) + 4 * B,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

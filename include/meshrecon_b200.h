@@ -123,7 +123,17 @@ int mr_set_use_farneback(mr_context *ctx, int on);
 int mr_process_main_frame_async(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                                 const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
                                 int *out_count);
-/* Block until every outstanding row copy of mr_process_main_frame_async has landed. */
+/* Fully asynchronous variant: enqueues the whole main-frame step and returns WITHOUT waiting for the GPU, so the
+ * host can queue many main frames back to back.  out_points and out_count (may be NULL) must be device memory
+ * or PINNED host memory (cudaHostAlloc / cudaHostRegister; torch pin_memory), both in the same memory space.
+ * Pinned buffers are filled by a copy-engine DMA of the full H*W*7-float capacity (the row count is not known on
+ * the host without a synchronisation; only the first *out_count rows are meaningful) that overlaps the next
+ * frames' compute.  Input frames in pinned host memory are uploaded asynchronously and, like the outputs, must
+ * stay alive and untouched until mr_synchronize() (or mr_wait_copies() after the stream has drained). */
+int mr_submit_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                         const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
+                         int *out_count);
+/* Block until every outstanding row copy of mr_process_main_frame_async / mr_submit_main_frame has landed. */
 int mr_wait_copies(mr_context *ctx);
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */

@@ -7,9 +7,9 @@ argument meaning, same in-place behaviour.  There is no CPU fallback: importing 
 anywhere, but every compute call needs the CUDA library and a B200.
 """
 from .api import (MeshReconError, Render, calculateFlow, compare, extractCameraCenter, flowRemap,  # noqa: F401
-                  imageGradient, library_path, load_library, mixBackground, process_main_frame, spawnRender,
+                  imageGradient, library_path, load_library, mixBackground, process_main_frame, spawnRender, submit_main_frame,
                   triangulatePixels)
 
 __all__ = ["MeshReconError", "Render", "calculateFlow", "compare", "extractCameraCenter", "flowRemap",
-           "imageGradient", "library_path", "load_library", "mixBackground", "process_main_frame", "spawnRender",
+           "imageGradient", "library_path", "load_library", "mixBackground", "process_main_frame", "spawnRender", "submit_main_frame",
            "triangulatePixels"]

@@ -67,6 +67,7 @@ def load_library():
     L.mr_process_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
     L.mr_process_main_frame_async.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
     L.mr_wait_copies.argtypes = [vp]
+    L.mr_submit_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, vp]
     L.mr_points_device.argtypes = [vp, ip]
     L.mr_points_device.restype = vp
     L.mr_last_depth_device.argtypes = [vp]
@@ -332,3 +333,20 @@ def process_main_frame(render, main_frame, main_camera, side_frames, side_camera
     if want_host and not async_copy and not _is_torch(out):
         return out[:m.value]
     return m.value
+
+
+def submit_main_frame(render, main_frame, main_camera, side_frames, side_cameras, out, out_count=None):
+    """Fully asynchronous ``mr_submit_main_frame``: returns immediately.  ``out`` (N x 7 float32) and
+    ``out_count`` (1 x int32) are torch tensors on the device or in pinned host memory; frames likewise (or NumPy
+    views of pinned tensors).  Call ``render.ctx.synchronize()`` before reading the results; keep every buffer alive
+    until then."""
+    ctx = render.ctx
+    S = len(side_frames)
+    keep = [_ptr(f, np.uint8) for f in side_frames]
+    arr = (C.c_void_p * S)(*[k[0] for k in keep])
+    pf, kf = _ptr(main_frame, np.uint8)
+    pm, km = _mat16(main_camera)
+    cams = np.ascontiguousarray(np.stack([np.asarray(c, np.float32).reshape(16) for c in side_cameras]))
+    po, ko = _ptr(out, np.float32)
+    pc = _ptr(out_count, np.int32)[0] if out_count is not None else None
+    ctx.check(ctx.lib.mr_submit_main_frame(ctx.h, pf, pm, S, arr, cams.ctypes.data, po, pc))

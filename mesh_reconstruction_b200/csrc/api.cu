@@ -145,6 +145,7 @@ void mr_destroy(mr_context *ctx)
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int i = 0; i < 2; i++) if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
+    for (int i = 0; i < 2; i++) if (ctx->ev_rows_done[i]) cudaEventDestroy(ctx->ev_rows_done[i]);
     for (auto &r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -449,13 +450,44 @@ int mr_extract_camera_center(const float camera[16], float out_center3[3])
     return MR_OK;
 }
 
+enum { PMF_SYNC = 0, PMF_ASYNC_COPY = 1, PMF_SUBMIT = 2 };
+
+static int ensure_copy_stream(mr_context *ctx)
+{
+    if (!ctx->copy_stream) {
+        // highest priority: the few CTAs of the device-side row copy must not queue behind full-grid compute kernels
+        int lo = 0, hi = 0;
+        MR_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MR_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 2; i++) {
+            MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
+            MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rows_done[i], cudaEventDisableTiming));
+        }
+    }
+    return MR_OK;
+}
+
+// device-visible alias of a user pointer: device memory as is, pinned (mapped) host memory through UVA
+static void *device_alias(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return const_cast<void *>(p);
+    if (a.type == cudaMemoryTypeHost) return a.devicePointer;
+    return nullptr;
+}
+
 static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                                    const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count,
-                                   bool async_copy)
+                                   int mode)
 {
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
-    CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && out_count, "null argument");
+    const bool async_copy = mode == PMF_ASYNC_COPY;
+    CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && (out_count || mode == PMF_SUBMIT), "null argument");
     CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
     if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
     size_t N = ctx->N;
@@ -487,16 +519,44 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         d_flows[i] = flow;
     }
     bool dev_out = out_points && mr_is_device_ptr(out_points);
+    if (mode == PMF_SUBMIT) {
+        // fully asynchronous: nothing below waits for the GPU; rows and count are delivered by device-side stores
+        CHECK_ARG(ctx, out_points, "mr_submit_main_frame needs an output buffer");
+        float *out_alias = (float *)device_alias(out_points);
+        int *cnt_alias = out_count ? (int *)device_alias(out_count) : nullptr;
+        CHECK_ARG(ctx, out_alias && (!out_count || cnt_alias), "mr_submit_main_frame: out_points / out_count must be device or pinned host memory");
+        CHECK_ARG(ctx, !out_count || mr_is_device_ptr(out_points) == mr_is_device_ptr(out_count), "mr_submit_main_frame: out_points and out_count must live in the same memory space");
+        RC(ensure_copy_stream(ctx));
+        if (dev_out) {
+            int *d_cnt = (cnt_alias && mr_is_device_ptr(out_count)) ? cnt_alias : mr_buf<int>(ctx, "count", 1);
+            RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, out_points, nullptr, cnt_alias ? cnt_alias : d_cnt));
+            return MR_OK;
+        }
+        const int slot = ctx->rows_cur;
+        float *d_rows = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
+        int *d_cnt = mr_buf<int>(ctx, slot ? "count1" : "count0", 1);
+        if (!d_rows || !d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_submit_main_frame", "alloc");
+        if (ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
+        RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_rows, nullptr, d_cnt));
+        MR_CUDA(ctx, cudaEventRecord(ctx->ev_rows_done[slot], ctx->stream));
+        MR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows_done[slot], 0));
+        // DMA (copy engine, no SMs) of the row buffer at full capacity -- the row count is not known on the host without
+        // a synchronisation, and a device-side copy kernel over PCIe measured only ~24 GB/s against ~52 GB/s for the
+        // DMA; only the first *out_count rows are meaningful.  58 MB at 1080p: hidden under the next frame's compute.
+        MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_rows, N * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_count) MR_CUDA(ctx, cudaMemcpyAsync(out_count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        MR_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+        ctx->copy_pending[slot] = true;
+        ctx->rows_cur = slot ^ 1;
+        return MR_OK;
+    }
     const bool pipelined = async_copy && out_points && !dev_out;
     float *d_out;
     int slot = 0;
     if (dev_out) d_out = out_points;
     else if (pipelined) {
         // ping-pong row buffers: the copy of slot s may still be in flight while slot s^1 is computed
-        if (!ctx->copy_stream) {
-            MR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; i++) MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
-        }
+        RC(ensure_copy_stream(ctx));
         slot = ctx->rows_cur;
         d_out = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
         if (d_out && ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
@@ -521,13 +581,19 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
 int mr_process_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                           const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
 {
-    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, false);
+    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, PMF_SYNC);
+}
+
+int mr_submit_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                         const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
+{
+    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, PMF_SUBMIT);
 }
 
 int mr_process_main_frame_async(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                                 const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count)
 {
-    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, true);
+    return process_main_frame_impl(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, out_count, PMF_ASYNC_COPY);
 }
 
 int mr_profile_enable(mr_context *ctx, int on)

@@ -69,6 +69,7 @@ struct mr_context {
     // pipelined device->host copies of point rows (mr_process_main_frame_async)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rows_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
     int rows_cur = 0;
     // profiling
@@ -162,6 +163,6 @@ int mr_flow_init_tables(mr_context *ctx);
 // tri.cu
 int k_image_gradient(mr_context *ctx, const float *d_img, float *d_grad2);
 int k_triangulate(mr_context *ctx, const float *const *d_flows_host_array, int S, const float *Pmain, const float *cams,
-                  const float *d_depth, float *d_out7, int *out_count);
+                  const float *d_depth, float *d_out7, int *out_count, int *d_count_out = nullptr);
 void mr_tri_const_init(TriConst *c, const float *Pmain, const float *cams, int S);
 void mr_camera_center(const float *P, float *c3);

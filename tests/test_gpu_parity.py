@@ -285,3 +285,32 @@ def test_farneback_branch(W, H):
         err = np.abs(tri[ok, :3] / tri[ok, 3:4] - ref[ok, :3] / ref[ok, 3:4])
         # Farneback's flow is only reproduced to ~1e-5 px, so the Newton result is not bit-identical here:
         assert np.percentile(err.max(1), 99) <= 1e-4 * sc.scale
+
+
+def test_submit_main_frame_is_async_and_equal():
+    """mr_submit_main_frame: several main frames queued without any host synchronisation, rows + counts delivered
+    to pinned host memory (device-side copy) and to device memory; identical to the synchronous call."""
+    import torch
+    W, H = 320, 240
+    sc = synth.make_scene(W, H, 5, seed=9, step=0.12, mesh_err=0.03, mesh_res=10)
+    frames = sc.frames()
+    r = mr.Render(W, H, ctx=mr.api.Context(W, H))
+    r.loadMesh(sc.vertices, sc.faces)
+    ref = [mr.process_main_frame(r, frames[i], sc.cameras[i], [frames[i + 1]], [sc.cameras[i + 1]]).copy() for i in range(4)]
+    fpin = [torch.from_numpy(f).pin_memory() for f in frames]
+    rows = [torch.empty((W * H, 7), dtype=torch.float32).pin_memory() for _ in range(4)]
+    cnt = torch.zeros(4, dtype=torch.int32).pin_memory()
+    for i in range(4):
+        mr.submit_main_frame(r, fpin[i], sc.cameras[i], [fpin[i + 1]], [sc.cameras[i + 1]], out=rows[i], out_count=cnt[i:i + 1])
+    r.ctx.synchronize()
+    for i in range(4):
+        assert int(cnt[i]) == len(ref[i])
+        assert np.array_equal(rows[i].numpy()[:len(ref[i])], ref[i], equal_nan=True)
+    drows = torch.empty((W * H, 7), dtype=torch.float32, device="cuda")
+    dcnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fdev = [torch.from_numpy(f).cuda() for f in frames]
+    mr.submit_main_frame(r, fdev[2], sc.cameras[2], [fdev[3]], [sc.cameras[3]], out=drows, out_count=dcnt)
+    r.ctx.synchronize()
+    assert int(dcnt.item()) == len(ref[2]) and np.array_equal(drows.cpu().numpy()[:len(ref[2])], ref[2], equal_nan=True)
+    with pytest.raises(mr.MeshReconError):       # pageable host output cannot be written asynchronously
+        mr.submit_main_frame(r, frames[0], sc.cameras[0], [frames[1]], [sc.cameras[1]], out=np.empty((W * H, 7), f32))
