@@ -11,6 +11,12 @@ thread_local std::string g_mr_create_error;
 int g_mr_vr_impl = 1;
 extern int g_mr_vr_tma;
 
+size_t &mr_smem_registry(int device, const void *kernel)
+{
+    static std::map<std::pair<int, const void *>, size_t> reg;   // calls on a context are serialised by the caller
+    return reg[std::make_pair(device, kernel)];
+}
+
 int mr_fail(mr_context *ctx, int code, const char *what, const char *detail)
 {
     std::string msg = std::string(what ? what : "") + ": " + (detail ? detail : "");

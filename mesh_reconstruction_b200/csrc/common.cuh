@@ -142,6 +142,19 @@ int mr_out(mr_context *ctx, void *dst, const void *src_dev, size_t bytes);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel (shared by every context of
+// this process on that device): keep one registry per (device, kernel) and only ever raise the limit.
+size_t &mr_smem_registry(int device, const void *kernel);   // api.cu
+template <class K>
+static inline cudaError_t mr_ensure_smem(mr_context *ctx, K kernel, size_t bytes)
+{
+    size_t &have = mr_smem_registry(ctx->device, (const void *)kernel);
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 // ---- stage launchers (all enqueue on ctx->stream; device pointers only) ------------
 // raster.cu
 int k_load_mesh(mr_context *ctx, const float *d_vtx, const int32_t *d_faces, int F);

@@ -431,11 +431,7 @@ int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, flo
             if (l >= t) { g.off[l] = off; off += ctx->lw[l] * ctx->lh[l]; }
         }
         size_t smem = (size_t)g.total * 3 * sizeof(float);
-        static size_t attr_set = 0;
-        if (smem > attr_set) {
-            MR_CUDA(ctx, cudaFuncSetAttribute(pyr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = smem;
-        }
+        MR_CUDA(ctx, mr_ensure_smem(ctx, pyr_tail_kernel, smem));
         pyr_tail_kernel<<<1, 1024, smem, ctx->stream>>>(pa + ctx->loff[t - 1], pb + ctx->loff[t - 1], g, pd + ctx->loff[t]);
         MR_LAUNCH_CHECK(ctx, "pyr_tail_kernel");
     }

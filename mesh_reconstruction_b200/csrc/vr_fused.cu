@@ -295,11 +295,7 @@ int launch(mr_context *ctx, const uint8_t *g0, const uint8_t *g1, const CUtensor
            const float *dv_in, float *du_out, float *dv_out, float4 *flow4)
 {
     auto kern = vr_fused_kernel<FIRST, LAST, USE_TMA>;
-    static bool attr = false;
-    if (!attr) {
-        MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        attr = true;
-    }
+    MR_CUDA(ctx, mr_ensure_smem(ctx, kern, sizeof(Smem)));
     dim3 grid(cdiv(ctx->W, OTW), cdiv(ctx->H, OTH));
     kern<<<grid, NT, sizeof(Smem), ctx->stream>>>(g0, g1, tm0, tm1, du_in, dv_in, du_out, dv_out, flow4, ctx->W, ctx->H);
     MR_LAUNCH_CHECK(ctx, "vr_fused_kernel");

@@ -314,3 +314,28 @@ def test_submit_main_frame_is_async_and_equal():
     assert int(dcnt.item()) == len(ref[2]) and np.array_equal(drows.cpu().numpy()[:len(ref[2])], ref[2], equal_nan=True)
     with pytest.raises(mr.MeshReconError):       # pageable host output cannot be written asynchronously
         mr.submit_main_frame(r, frames[0], sc.cameras[0], [frames[1]], [sc.cameras[1]], out=np.empty((W * H, 7), f32))
+
+
+def test_device_pointers_in_and_out():
+    """Every buffer argument may be a device pointer (torch CUDA tensors): zero-copy in, rows written in place."""
+    import torch
+    W, H = 320, 240
+    sc = synth.make_scene(W, H, 3, seed=2, step=0.12, mesh_err=0.03, mesh_res=10)
+    frames = sc.frames()
+    r = mr.spawnRender(W, H)
+    r.loadMesh(torch.from_numpy(sc.vertices).cuda(), torch.from_numpy(sc.faces).cuda())
+    ref = mr.process_main_frame(r, frames[1], sc.cameras[1], [frames[0], frames[2]], [sc.cameras[0], sc.cameras[2]]).copy()
+    fd = [torch.from_numpy(f).cuda() for f in frames]
+    out = torch.full((W * H, 7), -7.0, dtype=torch.float32, device="cuda")
+    m = mr.process_main_frame(r, fd[1], sc.cameras[1], [fd[0], fd[2]], [sc.cameras[0], sc.cameras[2]], out=out, want_host=False)
+    r.ctx.synchronize()
+    assert m == len(ref) and np.array_equal(out[:m].cpu().numpy(), ref, equal_nan=True)
+    assert float(out[m:].min()) == -7.0 and float(out[m:].max()) == -7.0           # nothing written past the count
+    depth = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    r.depth(sc.cameras[1], out=depth)
+    r.ctx.synchronize()
+    assert np.array_equal(depth.cpu().numpy(), r.depth(sc.cameras[1]))
+    flow = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    mr.calculateFlow(fd[0], fd[1], out=flow)
+    r.ctx.synchronize()
+    assert np.array_equal(flow.cpu().numpy(), mr.calculateFlow(frames[0], frames[1]))
