@@ -232,18 +232,29 @@ __device__ __forceinline__ int refl101(int i, int n)
     return i;
 }
 
+// One output sample of cv::pyrDown (float arithmetic).  OpenCV computes some output columns with its 4-lane SIMD body
+// and some with scalar code, and the two associate the five taps differently; to be BIT-EXACT with it the same split
+// is reproduced (oracle/cvprims.py::pyr_down, verified against cv2):
+//   horizontal: columns 1 .. 4*floor((width0-1)/4) SIMD, others scalar, width0 = min((w-3)/2 + 1, wo)
+//   vertical  : columns < 4*floor(wo/4) SIMD, others scalar
 template <class T>
 __device__ __forceinline__ float pyr_down_at(const T *__restrict__ src, int w, int h, int X, int Y)
 {
+    const int wo = (w + 1) / 2;
+    const int width0 = min((w - 3) / 2 + 1, wo);
+    const int nvec_h = (width0 - 1 >= 4) ? ((width0 - 1) / 4) * 4 : 0;
+    const bool hsimd = X >= 1 && X < 1 + nvec_h;
+    const bool vsimd = X < (wo / 4) * 4;
     float R[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const T *r = src + (size_t)refl101(2 * Y + k - 2, h) * w;
         float r0 = (float)r[refl101(2 * X - 2, w)], r1 = (float)r[refl101(2 * X - 1, w)], r2 = (float)r[refl101(2 * X, w)];
         float r3 = (float)r[refl101(2 * X + 1, w)], r4 = (float)r[refl101(2 * X + 2, w)];
-        R[k] = r2 * 6.f + ((r1 + r3) * 4.f + (r0 + r4));
+        R[k] = hsimd ? r2 * 6.f + ((r1 + r3) * 4.f + (r0 + r4)) : ((r2 * 6.f + (r1 + r3) * 4.f) + r0) + r4;
     }
-    return (((R[1] + R[3]) + R[2]) * 4.f + ((R[0] + R[4]) + (R[2] + R[2]))) * (1.f / 256.f);
+    return vsimd ? (((R[1] + R[3]) + R[2]) * 4.f + ((R[0] + R[4]) + (R[2] + R[2]))) * (1.f / 256.f)
+                 : (((R[2] * 6.f + (R[1] + R[3]) * 4.f) + R[0]) + R[4]) * (1.f / 256.f);
 }
 
 // level l -> l+1 for both images, plus the L1 difference of the new level
@@ -271,12 +282,26 @@ __global__ void absdiff_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *
 
 __device__ __forceinline__ float pyr_up_row(const float *__restrict__ r, int w, int X)
 {
-    // horizontally up-sampled value at column X (0 <= X < 2w) of low-res row r
+    // horizontally up-sampled value at column X (0 <= X < 2w) of low-res row r, exactly as cv::pyrUp evaluates it
     int x = X >> 1;
-    int xr = min(x + 1, w - 1);
-    if (X & 1) return (r[x] + r[xr]) * 4.f;
-    int xl = (w > 1) ? (x == 0 ? 1 : x - 1) : 0;
-    return (r[xl] + r[x] * 6.f) + r[xr];
+    if (w == 1) return r[0] * 8.f;
+    if (X & 1) return (x == w - 1) ? r[w - 1] * 8.f : (r[x] + r[x + 1]) * 4.f;
+    if (x == 0) return r[0] * 6.f + r[1] * 2.f;
+    if (x == w - 1) return r[w - 2] + r[w - 1] * 7.f;
+    return (r[x - 1] + r[x] * 6.f) + r[x + 1];
+}
+
+// vertical part of cv::pyrUp at output row Y (H rows out of h): rows 2h (H = 2h+1) repeat row 2h-2
+__device__ __forceinline__ float pyr_up_at(const float *__restrict__ src, int w, int h, int X, int Y)
+{
+    const int Xc = min(X, 2 * w - 1);                       // W = 2w+1: last column repeats column 2w-1
+    const int Yc = (Y >= 2 * h) ? 2 * h - 2 : Y;
+    const int y = Yc >> 1, yd = min(y + 1, h - 1);
+    const float r1 = pyr_up_row(src + (size_t)y * w, w, Xc), r2 = pyr_up_row(src + (size_t)yd * w, w, Xc);
+    if (Yc & 1) return ((r1 + r2) * 4.f) * (1.f / 64.f);
+    const int yu = (h > 1) ? (y == 0 ? 1 : y - 1) : 0;
+    const float r0 = pyr_up_row(src + (size_t)yu * w, w, Xc);
+    return ((r0 + r1 * 6.f) + r2) * (1.f / 64.f);
 }
 
 // dst (W x H, level l) += pyrUp(src (w x h, level l+1)); writes into `out` with a pixel stride
@@ -287,18 +312,7 @@ __global__ void __launch_bounds__(256) pyr_up_add_kernel(const float *__restrict
     int X = blockIdx.x * blockDim.x + threadIdx.x;
     int Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= W || Y >= H) return;
-    int Xc = min(X, 2 * w - 1), Yc = min(Y, 2 * h - 1);  // odd sizes duplicate the last column / row
-    int y = Yc >> 1;
-    int yd = min(y + 1, h - 1);
-    float v;
-    float r1 = pyr_up_row(src + (size_t)y * w, w, Xc);
-    float r2 = pyr_up_row(src + (size_t)yd * w, w, Xc);
-    if (Yc & 1) v = (r1 + r2) * (1.f / 16.f);
-    else {
-        int yu = (h > 1) ? (y == 0 ? 1 : y - 1) : 0;
-        float r0 = pyr_up_row(src + (size_t)yu * w, w, Xc);
-        v = ((r1 * 6.f + r0) + r2) * (1.f / 64.f);
-    }
+    const float v = pyr_up_at(src, w, h, X, Y);
     size_t i = (size_t)Y * W + X;
     out[i * out_stride + out_off] = dst[i] + v;
 }
@@ -369,15 +383,7 @@ __global__ void __launch_bounds__(1024) pyr_tail_kernel(const float *__restrict_
         float *dst = D + g.off[l];
         for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
             int X = i % W, Y = i / W;
-            int Xc = min(X, 2 * w - 1), Yc = min(Y, 2 * h - 1);
-            int y = Yc >> 1, yd = min(y + 1, h - 1);
-            float r1 = pyr_up_row(src + y * w, w, Xc), r2 = pyr_up_row(src + yd * w, w, Xc), v;
-            if (Yc & 1) v = (r1 + r2) * (1.f / 16.f);
-            else {
-                int yu = (h > 1) ? (y == 0 ? 1 : y - 1) : 0;
-                float r0 = pyr_up_row(src + yu * w, w, Xc);
-                v = ((r1 * 6.f + r0) + r2) * (1.f / 64.f);
-            }
+            const float v = pyr_up_at(src, w, h, X, Y);
             dst[i] = dst[i] + v;
         }
         __syncthreads();

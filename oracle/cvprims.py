@@ -13,7 +13,7 @@ function               reference call site         agreement with cv2 4.13
 =====================  ==========================  ==============================
 variational_refinement flow.cpp:29,32              bit-exact (all sizes tested)
 remap_cubic_8u         util.cpp:401                bit-exact
-pyr_down / pyr_up      util.cpp:348-349,356        float rounding (SIMD interior exact)
+pyr_down / pyr_up      util.cpp:348-349,356        bit-exact (incl. OpenCV's SIMD/scalar column split)
 sobel_gradient         util.cpp:473-474            float rounding (SIMD interior exact)
 lu_inv4                util.cpp:174                bit-exact
 inv2                   util.cpp:222                bit-exact
@@ -236,52 +236,79 @@ def _refl101(i, n):
     return np.where(i >= n, 2 * (n - 1) - i, i)
 
 
+def _refl101_scalar(i, n):
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        if i < 0:
+            i = -i
+        if i >= n:
+            i = 2 * (n - 1) - i
+    return i
+
+
 def pyr_down(src):
-    """[1 4 6 4 1]/16 separable, BORDER_REFLECT_101, out ((W+1)/2, (H+1)/2).
-    Association = OpenCV's SIMD body (interior bit-exact; OpenCV's scalar
-    border/tail columns use another association and may differ by 1 ulp)."""
+    """``cv::pyrDown`` on float32: [1 4 6 4 1]/16 separable, BORDER_REFLECT_101, out ((W+1)/2, (H+1)/2).
+
+    BIT-EXACT against cv2 4.13 (tests/test_oracle_cv.py), which requires reproducing which output columns
+    OpenCV computes with its 4-lane SIMD body and which with its scalar code, because the two associate the
+    five taps differently:
+      horizontal  SIMD   c*6 + ((l + r)*4 + (ll + rr))      columns 1 .. 4*floor((width0-1)/4)
+                  scalar ((c*6 + (l + r)*4) + ll) + rr      column 0, the remaining ones, and the right border
+                                                            (width0 = min((W-3)/2 + 1, Wd))
+      vertical    SIMD   ((r1 + r3 + r2)*4 + (r0 + r4 + (r2 + r2))) / 256     columns < 4*floor(Wd/4)
+                  scalar (((r2*6 + (r1 + r3)*4) + r0) + r4) / 256             the rest"""
     src = src.astype(f32)
     H, W = src.shape
     Wd, Hd = (W + 1) // 2, (H + 1) // 2
-    xs = np.arange(Wd) * 2
-    r = [src[:, _refl101(xs + k, W)] for k in (-2, -1, 0, 1, 2)]
-    row = r[2] * f32(6) + ((r[1] + r[3]) * f32(4) + (r[0] + r[4]))
-    ys = np.arange(Hd) * 2
-    r = [row[_refl101(ys + k, H), :] for k in (-2, -1, 0, 1, 2)]
-    return (((r[1] + r[3] + r[2]) * f32(4) + (r[0] + r[4] + (r[2] + r[2]))) * f32(1.0 / 256)).astype(f32)
+    width0 = min(int((W - 3) / 2) + 1, Wd)            # C integer division truncates toward zero
+    nvec_h = ((width0 - 1) // 4) * 4 if width0 - 1 >= 4 else 0
+    xs = np.arange(Wd)
+    idx = [np.array([_refl101_scalar(2 * x + k, W) for x in range(Wd)]) for k in (-2, -1, 0, 1, 2)]
+    s0, s1, s2, s3, s4 = [src[:, i] for i in idx]
+    simd = s2 * f32(6) + ((s1 + s3) * f32(4) + (s0 + s4))
+    scal = ((s2 * f32(6) + (s1 + s3) * f32(4)) + s0) + s4
+    row = np.where(((xs >= 1) & (xs < 1 + nvec_h))[None, :], simd, scal)
+    idy = [np.array([_refl101_scalar(2 * y + k, H) for y in range(Hd)]) for k in (-2, -1, 0, 1, 2)]
+    r0, r1, r2, r3, r4 = [row[i, :] for i in idy]
+    simd = ((r1 + r3 + r2) * f32(4) + (r0 + r4 + (r2 + r2))) * f32(1.0 / 256)
+    scal = (((r2 * f32(6) + (r1 + r3) * f32(4)) + r0) + r4) * f32(1.0 / 256)
+    return np.where((xs < (Wd // 4) * 4)[None, :], simd, scal).astype(f32)
 
 
 def pyr_up(src, dsize):
-    """Zero-insert x2 then [1 4 6 4 1]/8 per axis (``cv::pyrUp``), output size
-    ``dsize=(H, W)`` with |H - 2h| <= 1 (odd sizes replicate the last row/col).
-    Low-res borders: reflect-101 on the left/top, replicate on right/bottom."""
+    """``cv::pyrUp`` on float32 to ``dsize=(H, W)`` (|H - 2h| <= 1, |W - 2w| <= 1).  BIT-EXACT against cv2 4.13.
+      horizontal  even 2x : (s[x-1] + s[x]*6) + s[x+1]; x = 0: s[0]*6 + s[1]*2; x = w-1: s[w-2] + s[w-1]*7
+                  odd 2x+1: (s[x] + s[x+1])*4;          x = w-1: s[w-1]*8;      w = 1: both s*8
+      vertical    even 2y : ((r[y-1] + r[y]*6) + r[y+1]) / 64   (row -1 -> 1, row h -> h-1)
+                  odd 2y+1: ((r[y] + r[y+1])*4) / 64
+      odd sizes   W = 2w+1: last column repeats column 2w-1; H = 2h+1: last row repeats row 2h-2;
+                  W = 2w-1 / H = 2h-1: the surplus odd column / row is dropped."""
     src = src.astype(f32)
     h, w = src.shape
     H, W = dsize
-    xs = np.arange(w)
-    xl = _refl101(xs - 1, w) if w > 1 else np.zeros(w, int)
-    xr = np.minimum(xs + 1, w - 1)
-    # special-cased left border in OpenCV: reflect101(-1) -> 1  (w>1)
-    a, b, c = src[:, xl], src, src[:, xr]
-    even = a + b * f32(6) + c
-    odd = (b + c) * f32(4)
-    row = np.empty((h, 2 * w), f32)
-    row[:, 0::2] = even
-    row[:, 1::2] = odd
-    ys = np.arange(h)
-    yu = _refl101(ys - 1, h) if h > 1 else np.zeros(h, int)
-    yd = np.minimum(ys + 1, h - 1)
-    r0, r1, r2 = row[yu, :], row, row[yd, :]
-    ev = ((r1 * f32(6) + r0) + r2) * f32(1.0 / 64)
-    od = (r1 + r2) * f32(1.0 / 16)
-    out = np.empty((2 * h, 2 * w), f32)
-    out[0::2] = ev
-    out[1::2] = od
-    # odd destination sizes: OpenCV duplicates the last column / row
+    row = np.zeros((h, max(W, 2 * w)), f32)
+    if w == 1:
+        row[:, 0] = src[:, 0] * f32(8)
+        row[:, 1] = src[:, 0] * f32(8)
+    else:
+        a, b, c = src[:, :-2], src[:, 1:-1], src[:, 2:]
+        row[:, 2:2 * w - 2:2] = a + b * f32(6) + c
+        row[:, 3:2 * w - 1:2] = (b + c) * f32(4)
+        row[:, 0] = src[:, 0] * f32(6) + src[:, 1] * f32(2)
+        row[:, 1] = (src[:, 0] + src[:, 1]) * f32(4)
+        row[:, 2 * w - 2] = src[:, w - 2] + src[:, w - 1] * f32(7)
+        row[:, 2 * w - 1] = src[:, w - 1] * f32(8)
     if W > 2 * w:
-        out = np.concatenate([out, out[:, -1:]], 1)
+        row[:, W - 1] = row[:, 2 * w - 1]
+    yu = np.array([_refl101_scalar(2 * (y - 1), 2 * h) // 2 for y in range(h)])
+    yd = np.array([_refl101_scalar(2 * (y + 1), 2 * h) // 2 for y in range(h)])
+    r0, r1, r2 = row[yu], row, row[yd]
+    out = np.zeros((max(H, 2 * h), row.shape[1]), f32)
+    out[1:2 * h:2] = ((r1 + r2) * f32(4)) * f32(1.0 / 64)
+    out[0:2 * h:2] = ((r0 + r1 * f32(6)) + r2) * f32(1.0 / 64)
     if H > 2 * h:
-        out = np.concatenate([out, out[-1:, :]], 0)
+        out[2 * h] = out[2 * h - 2]
     return out[:H, :W].astype(f32)
 
 
