@@ -14,7 +14,7 @@ function               reference call site         agreement with cv2 4.13
 variational_refinement flow.cpp:29,32              bit-exact (all sizes tested)
 remap_cubic_8u         util.cpp:401                bit-exact
 pyr_down / pyr_up      util.cpp:348-349,356        bit-exact (incl. OpenCV's SIMD/scalar column split)
-sobel_gradient         util.cpp:473-474            float rounding (SIMD interior exact)
+sobel_gradient         util.cpp:473-474            bit-exact (incl. OpenCV's SIMD/scalar column split)
 lu_inv4                util.cpp:174                bit-exact
 inv2                   util.cpp:222                bit-exact
 gemm_f32               util.cpp:86,89,99,209,219   bit-exact (small-matrix rule)
@@ -346,14 +346,27 @@ def compare_levels(h, w):
 # imageGradient  util.cpp:465-479  (cv::Sobel 3x3, CV_32F, BORDER_REFLECT_101)
 # --------------------------------------------------------------------------
 def sobel_gradient(img):
-    """Returns H x W x 2 float32 (gx, gy). Row filter first, then the column
-    filter in OpenCV's SIMD association ``(a + c) + 2*b``."""
+    """Returns H x W x 2 float32 (gx, gy), BIT-EXACT against cv2.Sobel (ksize 3, CV_32F, BORDER_REFLECT_101).
+    Row filter first, then the column filter.  The [1 2 1] smoothing is associated differently by OpenCV's 8-lane
+    SIMD body and by its scalar tail:
+      gx (column filter over the row differences d):  (d0 + d2) + 2*d1   columns < 8*floor(W/8)
+                                                      (d0 + 2*d1) + d2   the tail columns
+      gy (row filter l, c, r, then column difference): (l + r) + 2*c      columns < 8*floor(W/8) and a final
+                                                                          unpaired tail column
+                                                      (l + 2*c) + r      the tail columns taken in pairs"""
     img = img.astype(f32)
-    p = np.pad(img, 1, mode="reflect")
+    H, W = img.shape
+    p = np.pad(img, 1, mode="reflect") if min(H, W) > 1 else np.pad(img, 1, mode="edge")
+    xs = np.arange(W)
+    t0 = (W // 8) * 8
+    tail = (xs >= t0)[None, :]
     dxr = p[:, 2:] - p[:, :-2]
-    gx = (dxr[:-2] + dxr[2:]) + dxr[1:-1] * f32(2)
-    sxr = (p[:, :-2] + p[:, 2:]) + p[:, 1:-1] * f32(2)
-    gy = sxr[2:] - sxr[:-2]
+    gx = np.where(tail, dxr[:-2] + dxr[1:-1] * f32(2) + dxr[2:], (dxr[:-2] + dxr[2:]) + dxr[1:-1] * f32(2))
+    npair = ((W - t0) // 2) * 2
+    tailp = ((xs >= t0) & (xs < t0 + npair))[None, :]
+    l, c, r = p[:, :-2], p[:, 1:-1], p[:, 2:]
+    sx = np.where(tailp, l + c * f32(2) + r, (l + r) + c * f32(2))
+    gy = sx[2:] - sx[:-2]
     return np.stack([gx, gy], -1).astype(f32)
 
 

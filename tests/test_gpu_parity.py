@@ -176,7 +176,7 @@ def test_primitives_against_oracle():
         d = rng.random((H, W)).astype(f32)
         d[rng.random((H, W)) < 0.2] = 1.0
         g, gr = mr.imageGradient(d), flow.image_gradient(d)
-        assert np.allclose(g, gr, rtol=0, atol=2e-6) and (g != gr).mean() < 0.05                 # a8
+        assert np.array_equal(g, gr)                                                                # a8 bit-exact vs cv2.Sobel
     c = synth.make_scene(64, 48, 3).cameras[1]
     from oracle import native
     ref = np.empty(3, f32)
