@@ -161,6 +161,8 @@ def test_full_size_properties(W, H, S, with_oracle):
         ref, inter = _oracle_main(sc, frames, fa, sides)
         assert np.array_equal(flows[0][..., :2], inter["flows"][0][..., :2])
         _assert_rows(a, ref, sc.scale, "1080p vs oracle")
+        fin = np.isfinite(ref[:, :4]).all(1)
+        assert np.array_equal(a[fin, :4], ref[fin, :4])
 
 
 def test_depth_samples_match_full_depth_maps():

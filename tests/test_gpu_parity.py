@@ -25,7 +25,9 @@ def _oracle():
     return flow, pipeline, render, tri
 
 
-def _points_close(got, ref, scale, what=""):
+def _points_close(got, ref, scale, what="", exact=False):
+    """3-D points within 1e-4 of the scene scale (north_star); with exact=True additionally every finite row's
+    (x, y, z, w) must be BIT-IDENTICAL to the oracle's (all inputs of the Newton iteration are bit-exact)."""
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     nan_g, nan_r = np.isnan(got).any(1), np.isnan(ref).any(1)
     assert np.array_equal(nan_g, nan_r), what + ": NaN rows differ"
@@ -34,6 +36,9 @@ def _points_close(got, ref, scale, what=""):
     Xr = ref[ok, :3].astype(np.float64) / ref[ok, 3:4]
     err = np.abs(Xg - Xr).max() if ok.any() else 0.0
     assert err <= POINT_TOL_REL * scale, f"{what}: point error {err} > {POINT_TOL_REL * scale}"
+    if exact:
+        fin = np.isfinite(ref[:, :4]).all(1)
+        assert np.array_equal(got[fin, :4], ref[fin, :4]), what + ": finite point rows are not bit-identical"
     return err
 
 
@@ -98,13 +103,13 @@ def test_golden_stage_by_stage(golden_dir, name):
     assert np.array_equal(depth, g["depth"])
     # a10-a12 on the ORACLE's flows (isolates triangulation), then on our own flows
     tri = mr.triangulatePixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"])
-    _points_close(tri, g["tri"], scale, "tri(oracle flows)")
+    _points_close(tri, g["tri"], scale, "tri(oracle flows)", exact=True)
     _, _, _, otri = _oracle()
     ref_tri, evals = otri.triangulate_pixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"], return_evals=True)
     assert np.array_equal(ref_tri, g["tri"], equal_nan=True)
     _normals_close(tri, g["tri"], "tri(oracle flows)", evals)
     tri2 = mr.triangulatePixels(flows, cams[fa], [cams[s] for s in sides], depth)
-    _points_close(tri2, g["tri"], scale, "tri(own flows)")
+    _points_close(tri2, g["tri"], scale, "tri(own flows)", exact=True)
 
 
 @pytest.mark.parametrize("name", ["scene_s2_96x72", "scene_s1_128x96"])
@@ -115,7 +120,7 @@ def test_golden_fused_main_frame(golden_dir, name):
     r.loadMesh(g["vertices"], g["faces"])
     tri = mr.process_main_frame(r, g["frames"][fa], g["cameras"][fa], [g["frames"][s] for s in sides],
                                 [g["cameras"][s] for s in sides])
-    _points_close(tri, g["tri"], float(g["scale"]), "fused")
+    _points_close(tri, g["tri"], float(g["scale"]), "fused", exact=True)
     _normals_close(tri, g["tri"], "fused")
 
 
@@ -144,7 +149,7 @@ def test_seeded_scene_against_oracle(W, H, S):
         assert np.array_equal(mixed, inter["mixed"][i])
     depth = _device_to_numpy(ctx.lib.mr_last_depth_device(ctx.h), (H, W), np.float32)
     assert np.array_equal(depth, inter["depth"])
-    _points_close(got, ref, sc.scale, "pipeline")
+    _points_close(got, ref, sc.scale, "pipeline", exact=True)
     _normals_close(got, ref, "pipeline", inter["evals"])
 
 
