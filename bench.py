@@ -342,7 +342,8 @@ def main():
                        "pairs_per_step_per_gpu": B, "contexts_per_gpu": nctx, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
                        "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
                        "exchange": "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step" if world > 1 else "none (single GPU)"},
-            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": int(m_mean * 28 * B) + 4 * B,
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": (N * 28 + 4) * B,   # the DMA moves the full row capacity (count unknown on the host without a sync)
+                    "rows_bytes_per_step": int(m_mean * 28 * B),
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
