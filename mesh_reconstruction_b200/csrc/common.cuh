@@ -171,7 +171,6 @@ int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t
 int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const uint8_t *d_img, uint8_t *d_out);
 int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off);
 int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4);   // farneback.cu
-int k_zero_channel(mr_context *ctx, float *d_flow4, int channel);
 int mr_flow_init_tables(mr_context *ctx);
 // tri.cu
 int k_image_gradient(mr_context *ctx, const float *d_img, float *d_grad2);

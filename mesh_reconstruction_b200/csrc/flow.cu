@@ -458,14 +458,3 @@ int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, flo
     return MR_OK;
 }
 
-__global__ void zero_channel_kernel(float *flow4, size_t N, int ch)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) flow4[4 * i + ch] = 0.f;
-}
-int k_zero_channel(mr_context *ctx, float *d_flow4, int channel)
-{
-    zero_channel_kernel<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(d_flow4, ctx->N, channel);
-    MR_LAUNCH_CHECK(ctx, "zero_channel_kernel");
-    return MR_OK;
-}

@@ -11,9 +11,9 @@ What it restates (file:line are into the upstream reference tree):
 
 * ``flow.cpp:19-42``            -> :mod:`oracle.flow`      (calculateFlow, via the real OpenCV binary ``cv2``)
 * ``util.cpp:332-403,465-479``  -> :mod:`oracle.flow` / :mod:`oracle.cvprims` (compare, flowRemap, imageGradient)
-* ``util.cpp:33-53,62-329``     -> ``oracle/tri_oracle.c`` + :mod:`oracle.tri` (triangulatePixels / triangulatePixel)
+* ``util.cpp:33-53,62-329``     -> ``oracle/recon_oracle.c`` + :mod:`oracle.tri` (triangulatePixels / triangulatePixel)
 * ``util.cpp:366-387``          -> :mod:`oracle.render`    (mixBackground)
-* ``render_glx.cpp:230-397`` + ``shader.vert`` / ``shader.frag`` -> ``oracle/render_oracle.c`` + :mod:`oracle.render`
+* ``render_glx.cpp:230-397`` + ``shader.vert`` / ``shader.frag`` -> ``oracle/recon_oracle.c`` + :mod:`oracle.render`
 * ``recon.cpp:65-119``          -> :mod:`oracle.pipeline`  (the main/side loop)
 
 Parity pinning status
@@ -25,8 +25,14 @@ reference's own tests**.  What *is* pinned:
 
 * every OpenCV-owned primitive on the path (VariationalRefinement, remap
   INTER_CUBIC on 8U, pyrDown/pyrUp, Sobel, 4x4 / 2x2 ``invert``, small ``gemm``,
-  PCA) is executed by, or checked bit-for-bit / to float rounding against, the
-  real OpenCV binary (``cv2`` 4.13) in ``tests/test_oracle_cv.py``;
+  PCA) is executed by, or checked against, the real OpenCV binary (``cv2`` 4.13)
+  in ``tests/test_oracle_cv.py``: VariationalRefinement, remap, pyrDown / pyrUp /
+  ``compare``, Sobel, ``invert`` and ``gemm`` restatements are BIT-IDENTICAL to
+  cv2 (including its SIMD/scalar column split); PCA eigenvectors agree to float
+  rounding where the eigen-gap defines them;
+* the camera tracks and bundle points the reference ships (``tracks/*.yaml``) are
+  committed as golden inputs (``tests/golden/tracks_*.npz``, made by
+  ``tests/golden/make_yaml_fixtures.py``) and drive full-path parity tests;
 * the only concrete fixture the reference has on this path (the 25-vertex mesh
   and the two MVP matrices of ``render_glx.cpp:407-410``) is a committed golden
   input (``tests/golden``), with known-answer properties from Appendix E of

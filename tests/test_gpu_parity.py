@@ -16,7 +16,6 @@ pytestmark = pytest.mark.gpu
 f32 = np.float32
 FLOW_TOL_PX = 0.01          # north_star
 POINT_TOL_REL = 1e-4        # north_star: x scene scale
-VAR_TOL_REL = 1e-4          # variance: float-rounding level (OpenCV's own SIMD/scalar paths differ by this much)
 
 
 def _oracle():
