@@ -36,9 +36,10 @@ constexpr int IX_OFF = 16, IY_OFF = HALO + 1;              // image tile origin 
 constexpr int IPITCH = 96, IH = DH + 2;                    // image tile: 96 bytes x 86 rows
 constexpr int TY = 12;                                     // thread rows
 constexpr int NT = 512;                                    // threads per CTA (NP * TY = 504 active in the pair phases)
-constexpr int SLOTS = (DH - 2 + TY - 1) / TY;              // rows owned per thread (7)
+constexpr int SLOTS = (DH - 2 + TY - 1) / TY;              // rows owned per thread in the pair phases (7)
+constexpr int RSLOTS = DH / TY;                            // rows owned per thread in the staging phases (7)
 constexpr int PLANE = DH * NP;                             // floats per colour per plane
-static_assert(DW % 2 == 0 && NP * TY <= NT && (TY % 2) == 0, "thread layout");
+static_assert(DW % 2 == 0 && NP * TY <= NT && (TY % 2) == 0 && (HALO % 2) == 0 && (OTW % 2) == 0, "thread layout");
 static_assert(IX_OFF + OTW + HALO + 1 <= IPITCH, "image tile width");
 
 struct Smem {
@@ -50,6 +51,136 @@ struct Smem {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// du / dv of region D from the previous iteration (zero on the first one and outside the image), then the first
+// derivatives and the smoothness weights on D.  Same 42 x 12 layout as the pair phases: thread (tx, ty) owns
+// column pair tx of rows ty + 12k, k = 0..6 (DH == 7 * 12), so the colour of the pair's first column is ty & 1
+// for every slot and all 14 global loads of a thread are in flight together.
+template <bool INTERIOR, bool FIRST, bool USE_TMA>
+__device__ __forceinline__ void stage_phases(Smem &s, const int tid, const int dx0, const int dy0, const int ix0, const int iy0,
+                                             const int W, const int H, const float *__restrict__ du_in,
+                                             const float *__restrict__ dv_in)
+{
+    static_assert(DH == RSLOTS * TY, "row slots");
+    const int tx = tid % NP, ty = tid / NP;
+    const bool tact = tid < NP * TY;
+    const int pr = ty & 1;                                  // colour of column 2tx in every owned row
+    const int x0 = dx0 + 2 * tx;
+    if (tact) {
+        float2 u[RSLOTS], v[RSLOTS];
+        if (!FIRST) {
+            if ((W & 1) == 0) {                             // x0 is even: 8-byte aligned pairs when W is even
+                const bool xin = INTERIOR || (x0 >= 0 && x0 < W);
+#pragma unroll
+                for (int k = 0; k < RSLOTS; k++) {
+                    const int y = dy0 + ty + k * TY;
+                    u[k] = v[k] = make_float2(0.f, 0.f);
+                    if (xin && (INTERIOR || (y >= 0 && y < H))) {
+                        const size_t g = (size_t)y * W + x0;
+                        u[k] = __ldg(reinterpret_cast<const float2 *>(du_in + g));
+                        v[k] = __ldg(reinterpret_cast<const float2 *>(dv_in + g));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RSLOTS; k++) {
+                    const int y = dy0 + ty + k * TY;
+                    u[k] = v[k] = make_float2(0.f, 0.f);
+                    if (y >= 0 && y < H) {
+                        const size_t g = (size_t)y * W + x0;
+                        if (x0 >= 0 && x0 < W) { u[k].x = __ldg(du_in + g); v[k].x = __ldg(dv_in + g); }
+                        if (x0 + 1 >= 0 && x0 + 1 < W) { u[k].y = __ldg(du_in + g + 1); v[k].y = __ldg(dv_in + g + 1); }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RSLOTS; k++) {
+            const int idx = (ty + k * TY) * NP + tx;
+            if (FIRST) u[k] = v[k] = make_float2(0.f, 0.f);
+            s.du[pr][idx] = u[k].x;
+            s.du[pr ^ 1][idx] = u[k].y;
+            s.dv[pr][idx] = v[k].x;
+            s.dv[pr ^ 1][idx] = v[k].y;
+        }
+    }
+    if (USE_TMA) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&s.bar)) : "memory");
+    }
+    __syncthreads();
+
+    if (tact) {
+        const int lx = x0 - ix0;                            // I-local column of the pair (even)
+#pragma unroll
+        for (int k = 0; k < RSLOTS; k++) {
+            const int r = ty + k * TY;
+            const int y = dy0 + r;
+            const int idx = r * NP + tx;
+            float ix[2] = {0.f, 0.f}, iy[2] = {0.f, 0.f}, iz[2] = {0.f, 0.f}, w[2] = {0.f, 0.f};
+            if (INTERIOR) {
+                // rows y-1, y, y+1 of both frames: the pair as one 16-bit load, plus x-1 and x+2 on the centre row
+                const int ic = (y - iy0) * IPITCH + lx;
+                float a[4], zc[2], au[2], ad[2];
+#pragma unroll
+                for (int t = 0; t < 4; t++) a[t] = 0.5f * (float)s.i0[ic - 1 + t] + 0.5f * (float)s.i1[ic - 1 + t];
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    zc[t] = (float)s.i1[ic + t] - (float)s.i0[ic + t];
+                    au[t] = 0.5f * (float)s.i0[ic - IPITCH + t] + 0.5f * (float)s.i1[ic - IPITCH + t];
+                    ad[t] = 0.5f * (float)s.i0[ic + IPITCH + t] + 0.5f * (float)s.i1[ic + IPITCH + t];
+                }
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    ix[t] = a[t + 2] - a[t];
+                    iy[t] = ad[t] - au[t];
+                    iz[t] = zc[t];
+                }
+                if (r < DH - 1) {
+                    const float u0 = s.du[pr][idx], u1 = s.du[pr ^ 1][idx], v0 = s.dv[pr][idx], v1 = s.dv[pr ^ 1][idx];
+                    w[0] = vr_smooth_weight(u1 - u0, v1 - v0, s.du[pr ^ 1][idx + NP] - u0, s.dv[pr ^ 1][idx + NP] - v0);
+                    if (tx < NP - 1)
+                        w[1] = vr_smooth_weight(s.du[pr][idx + 1] - u1, s.dv[pr][idx + 1] - v1, s.du[pr][idx + NP] - u1,
+                                                s.dv[pr][idx + NP] - v1);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const int x = x0 + t, c = 2 * tx + t;
+                    const int col = pr ^ t, o = col ^ 1;
+                    if (x >= 0 && x < W && y >= 0 && y < H) {
+                        const int px = x - ix0, py = y - iy0;
+                        const int lxl = vr_clampi(x - 1, W) - ix0, lxr = vr_clampi(x + 1, W) - ix0;
+                        const int lyu = vr_clampi(y - 1, H) - iy0, lyd = vr_clampi(y + 1, H) - iy0;
+                        auto A = [&](int xx, int yy) { int i = yy * IPITCH + xx; return 0.5f * (float)s.i0[i] + 0.5f * (float)s.i1[i]; };
+                        ix[t] = A(lxr, py) - A(lxl, py);
+                        iy[t] = A(px, lyd) - A(px, lyu);
+                        const int i = py * IPITCH + px;
+                        iz[t] = (float)s.i1[i] - (float)s.i0[i];
+                        if (r < DH - 1 && c < DW - 1) {
+                            const float uu = s.du[col][idx], vv = s.dv[col][idx];
+                            float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
+                            const int ir = idx + t, id = idx + NP;
+                            if (x < W - 1) { ux = s.du[o][ir] - uu; vx = s.dv[o][ir] - vv; }
+                            if (y < H - 1) { uy = s.du[o][id] - uu; vy = s.dv[o][id] - vv; }
+                            w[t] = vr_smooth_weight(ux, vx, uy, vy);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                s.Ix[pr ^ t][idx] = ix[t];
+                s.Iy[pr ^ t][idx] = iy[t];
+                s.Iz[pr ^ t][idx] = iz[t];
+                s.ws[pr ^ t][idx] = w[t];
+            }
+        }
+    }
+    __syncthreads();
+}
 
 // Data term + red-black SOR for the pixels a thread owns.  INTERIOR tiles (tile + halo entirely inside
 // the image) drop every border predicate at compile time.
@@ -118,17 +249,28 @@ __device__ __forceinline__ void pair_phases(Smem &s, const int tid, const int dx
     }
 
     // ---- red-black SOR ---------------------------------------------------------------------------------------------
+    // Half-sweep hs (0 .. 2 * VR_SOR - 1) has to be right on tile + (2 * VR_SOR - 1 - hs) only: D-row r < HALO is
+    // needed while hs < r, row r > HALO + OTH - 1 while hs < DH - 1 - r.  (Skipping is as good as updating with
+    // stale neighbours: either way the row's values are never read by a pixel that still matters.)
+    static_assert(HALO == 2 * VR_SOR, "halo == dependency radius of the SOR sweeps");
+    const int row_first = 1 + ty, row_last = 1 + ty + (SLOTS - 1) * TY;
+    const int live_top = row_first < HALO ? row_first : 2 * VR_SOR;
+    const int live_bot = row_last > HALO + OTH - 1 ? DH - 1 - row_last : 2 * VR_SOR;
 #pragma unroll 1
     for (int sweep = 0; sweep < VR_SOR; sweep++) {
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const int o = col ^ 1;
+            const int hs = 2 * sweep + col;
             if (cact[col]) {
 #pragma unroll
                 for (int k = 0; k < SLOTS; k++) {
                     const int idx = base + k * TY * NP;
                     const int y = ystart + k * TY;
-                    const bool ract = (1 + ty + k * TY) <= DH - 2 && (INTERIOR || (y >= 0 && y < H));
+                    bool ract = (1 + ty + k * TY) <= DH - 2 && (INTERIOR || (y >= 0 && y < H));
+                    // halo rows stop mattering once the half-sweeps left cannot carry them into the tile
+                    if (k == 0) ract = ract && hs < live_top;
+                    if (k == SLOTS - 1) ract = ract && hs < live_bot;
                     if (ract) {
                         const int iL = idx + nl[col], iR = iL + 1, iU = idx - NP, iD = idx + NP;
                         float wsP = s.ws[col][idx];
@@ -186,71 +328,35 @@ __global__ void __launch_bounds__(NT, 1) vr_fused_kernel(const uint8_t *__restri
             s.i1[e] = b;
         }
     }
-    // ---- du / dv of region D from the previous iteration (zero on the first one and outside the image) ----
-    for (int e = tid; e < DH * DW; e += NT) {
-        int r = e / DW, c = e % DW;
-        int x = dx0 + c, y = dy0 + r;
-        float u = 0.f, v = 0.f;
-        if (!FIRST && x >= 0 && x < W && y >= 0 && y < H) { u = du_in[(size_t)y * W + x]; v = dv_in[(size_t)y * W + x]; }
-        int col = (r + c) & 1, idx = r * NP + (c >> 1);
-        s.du[col][idx] = u;
-        s.dv[col][idx] = v;
-    }
-    if (USE_TMA) {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(smem_u32(&s.bar)) : "memory");
-    }
-    __syncthreads();
-
-    // ---- first derivatives + smoothness weights on D -----------------------------------------------------------
-    for (int e = tid; e < DH * DW; e += NT) {
-        int r = e / DW, c = e % DW;
-        int x = dx0 + c, y = dy0 + r;
-        int col = (r + c) & 1, idx = r * NP + (c >> 1), o = col ^ 1;
-        float ix = 0.f, iy = 0.f, iz = 0.f, w = 0.f;
-        if (x >= 0 && x < W && y >= 0 && y < H) {
-            const int lx = x - ix0, ly = y - iy0;
-            const int lxl = vr_clampi(x - 1, W) - ix0, lxr = vr_clampi(x + 1, W) - ix0;
-            const int lyu = vr_clampi(y - 1, H) - iy0, lyd = vr_clampi(y + 1, H) - iy0;
-            auto A = [&](int xx, int yy) { int i = yy * IPITCH + xx; return 0.5f * (float)s.i0[i] + 0.5f * (float)s.i1[i]; };
-            ix = A(lxr, ly) - A(lxl, ly);
-            iy = A(lx, lyd) - A(lx, lyu);
-            int i = ly * IPITCH + lx;
-            iz = (float)s.i1[i] - (float)s.i0[i];
-            if (r < DH - 1 && c < DW - 1) {
-                float u = s.du[col][idx], v = s.dv[col][idx];
-                float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
-                int ir = r * NP + ((c + 1) >> 1), id = idx + NP;
-                if (x < W - 1) { ux = s.du[o][ir] - u; vx = s.dv[o][ir] - v; }
-                if (y < H - 1) { uy = s.du[o][id] - u; vy = s.dv[o][id] - v; }
-                w = vr_smooth_weight(ux, vx, uy, vy);
-            }
-        }
-        s.Ix[col][idx] = ix;
-        s.Iy[col][idx] = iy;
-        s.Iz[col][idx] = iz;
-        s.ws[col][idx] = w;
-    }
-    __syncthreads();
-
     // tile + halo + derivative taps inside the image?  (uniform per CTA)
     const bool interior = ix0 >= 0 && iy0 >= 0 && dx0 + DW + 1 <= W && dy0 + DH + 1 <= H;
+    if (interior) stage_phases<true, FIRST, USE_TMA>(s, tid, dx0, dy0, ix0, iy0, W, H, du_in, dv_in);
+    else stage_phases<false, FIRST, USE_TMA>(s, tid, dx0, dy0, ix0, iy0, W, H, du_in, dv_in);
+
     if (interior) pair_phases<true>(s, tid, dx0, dy0, W, H);
     else pair_phases<false>(s, tid, dx0, dy0, W, H);
 
-    // ---- write the tile -----------------------------------------------------------------------------------------------
-    for (int e = tid; e < OTH * OTW; e += NT) {
-        int tyy = e / OTW, txx = e % OTW;
-        int x = gx0 + txx, y = gy0 + tyy;
+    // ---- write the tile (column pairs; the pair's first column is even, so its colour is the row parity) -----
+    const bool vecw = (W & 1) == 0;
+    for (int e = tid; e < OTH * (OTW / 2); e += NT) {
+        const int tyy = e / (OTW / 2), p = e % (OTW / 2);
+        const int x = gx0 + 2 * p, y = gy0 + tyy;
         if (x < W && y < H) {
-            int r = tyy + HALO, c = txx + HALO;
-            int col = (r + c) & 1, idx = r * NP + (c >> 1);
-            float u = s.du[col][idx], v = s.dv[col][idx];
-            size_t g = (size_t)y * W + x;
-            if (LAST) flow4[g] = make_float4(u, v, 0.f, 0.f);
-            else { du_out[g] = u; dv_out[g] = v; }
+            const int r = tyy + HALO;
+            const int col = r & 1, idx = r * NP + p + HALO / 2;
+            const float u0 = s.du[col][idx], v0 = s.dv[col][idx], u1 = s.du[col ^ 1][idx], v1 = s.dv[col ^ 1][idx];
+            const size_t g = (size_t)y * W + x;
+            const bool second = x + 1 < W;
+            if (LAST) {
+                flow4[g] = make_float4(u0, v0, 0.f, 0.f);
+                if (second) flow4[g + 1] = make_float4(u1, v1, 0.f, 0.f);
+            } else if (vecw) {
+                *reinterpret_cast<float2 *>(du_out + g) = make_float2(u0, u1);
+                *reinterpret_cast<float2 *>(dv_out + g) = make_float2(v0, v1);
+            } else {
+                du_out[g] = u0; dv_out[g] = v0;
+                if (second) { du_out[g + 1] = u1; dv_out[g + 1] = v1; }
+            }
         }
     }
 }
