@@ -12,9 +12,10 @@ refinement -> cubic remap -> pyramid compare -> Newton triangulation -> PCA norm
 N > 1, the NCCL all-gather of the point rows.  Frame pairs shard across ranks (weak scaling).
 
 * `value`  : frames already resident in HBM when the timed region starts, point rows left in HBM.
-* `e2e`    : same call (`mr_process_main_frame` through the ctypes binding) with HOST buffers: frames
-             in pinned host memory (H2D inside the timed region) and the point rows copied back to
-             pinned host memory (D2H inside the timed region).
+* `e2e`    : same call (`mr_submit_main_frame` through the ctypes binding) with HOST buffers: frames
+             in pinned host memory (H2D inside the timed region) and every pair's point rows + count
+             copied back to pinned host memory (D2H inside the timed region; the host reads step s-1's
+             results while step s runs, the last step is drained before the region ends).
 * `roofline`: dominant kernel stage measured live with CUDA events on the library's stream.
 * `cpu_baseline`: the CPU oracle (cv2 for the OpenCV-owned arithmetic + C restatement) on a
              bounded sample of the same workload, on this box's host cores.
@@ -198,8 +199,10 @@ def main():
 
     nbuf = 2 if world > 1 else 1
     rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
-    rows_pin = [torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(B)]   # every pair of a step lands on the host
-    counts_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+    # every pair of a step lands on the host; two alternating sets so that the host reads step s-1 while step s runs
+    rows_pin = [[torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(B)] for _ in range(2)]
+    counts_pin = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    per_ctx = [len(range(c, B, nctx)) for c in range(nctx)]     # pairs each context gets per step
     counts = torch.zeros(B, dtype=torch.int64)
     rows_flat = [r.view(B * N, 7) for r in rows_dev]
     gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
@@ -240,14 +243,21 @@ def main():
 
     def step_e2e(s):
         # host frames in (pinned; H2D inside the call), every pair's point rows + count out to pinned host memory by the
-        # library's device-side copy (overlapping the next pairs' compute); the step ends when all B results are on the host
+        # library's copy-engine DMA (overlapping the next pairs' compute).  The host queues step s, then waits until every
+        # result of step s-1 has landed (mr_wait_copies_until: all but this step's copies) and reads it -- a two-deep
+        # pipeline of pinned buffer sets, the way a long-running reconstruction consumes its main frames.
+        k = s & 1
         for b in range(B):
             a, c = pair(s * B + b)
             mr.submit_main_frame(renders[b % nctx], frames_pin[a], cams[idx[a]], [frames_pin[c]], [cams[idx[c]]],
-                                 out=rows_pin[b], out_count=counts_pin[b:b + 1])
+                                 out=rows_pin[k][b], out_count=counts_pin[k][b:b + 1])
+        for c_, r_ in enumerate(renders):
+            r_.ctx.wait_copies_until(per_ctx[c_])
+        return int(counts_pin[k ^ 1].sum())
+
+    def drain_e2e():
         for r_ in renders:
-            r_.ctx.synchronize()
-        return int(counts_pin.sum())
+            r_.ctx.synchronize()          # the last step's rows are on the host before the timed region ends
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,7 +265,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, first):
+    def timed(fn, steps, first, drain=None):
         for k in range(nbuf):
             wait_pending(k)
         barrier()
@@ -264,6 +274,8 @@ def main():
         e0.record(lib_stream)
         for s in range(steps):
             fn(first + s)
+        if drain is not None:
+            drain()
         if world > 1:
             for k in range(nbuf):
                 wait_pending(k)           # the exchange of every timed step completes inside the timed region
@@ -284,8 +296,10 @@ def main():
     sampler.start()
     ms_res, launches = timed(step_resident, K, Wm)
     sampler.stop_flag = True
-    step_e2e(0)
-    ms_e2e, _ = timed(step_e2e, K, Wm)
+    for s in range(max(Wm - 2, 1)):
+        step_e2e(s)
+    drain_e2e()
+    ms_e2e, _ = timed(step_e2e, K, Wm, drain=drain_e2e)
     sampler.join(timeout=2)
 
     # ---- per-stage breakdown of one more step (events inside the library) -----------------------

@@ -135,6 +135,11 @@ int mr_submit_main_frame(mr_context *ctx, const uint8_t *main_frame, const float
                          int *out_count);
 /* Block until every outstanding row copy of mr_process_main_frame_async / mr_submit_main_frame has landed. */
 int mr_wait_copies(mr_context *ctx);
+/* Block until at most max_in_flight of the row copies queued so far are still outstanding (they complete in
+ * submission order): with a ring of R pinned output buffers per context, calling this with R - 1 before re-using a
+ * buffer -- or with the number of frames queued since the results one wants to read -- lets the host consume one
+ * main frame's rows while the following ones are still being computed and copied.  0 == mr_wait_copies. */
+int mr_wait_copies_until(mr_context *ctx, int max_in_flight);
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */
 const float *mr_points_device(mr_context *ctx, int *out_count);

@@ -67,6 +67,7 @@ def load_library():
     L.mr_process_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
     L.mr_process_main_frame_async.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
     L.mr_wait_copies.argtypes = [vp]
+    L.mr_wait_copies_until.argtypes = [vp, C.c_int]
     L.mr_submit_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, vp]
     L.mr_points_device.argtypes = [vp, ip]
     L.mr_points_device.restype = vp
@@ -130,6 +131,10 @@ class Context:
 
     def wait_copies(self):
         self.check(self.lib.mr_wait_copies(self.h))
+
+    def wait_copies_until(self, max_in_flight):
+        """Block until at most ``max_in_flight`` of the queued row copies are still outstanding."""
+        self.check(self.lib.mr_wait_copies_until(self.h, int(max_in_flight)))
 
     @property
     def stream(self):

@@ -152,6 +152,7 @@ void mr_destroy(mr_context *ctx)
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int i = 0; i < 2; i++) if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
     for (int i = 0; i < 2; i++) if (ctx->ev_rows_done[i]) cudaEventDestroy(ctx->ev_rows_done[i]);
+    for (auto e : ctx->ev_copy_ring) if (e) cudaEventDestroy(e);
     for (auto &r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -178,6 +179,20 @@ int mr_wait_copies(mr_context *ctx)
     SET_DEVICE(ctx);
     if (ctx->copy_stream) MR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+    return MR_OK;
+}
+
+int mr_wait_copies_until(mr_context *ctx, int max_in_flight)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, max_in_flight >= 0, "max_in_flight must be >= 0");
+    if (!ctx->copy_stream || ctx->copy_seq <= (unsigned long long)max_in_flight) return MR_OK;
+    // copies complete in submission order: waiting for number `last` covers every earlier one.  A target that has
+    // already left the ring is covered by the oldest event still in it.
+    unsigned long long last = ctx->copy_seq - 1 - (unsigned long long)max_in_flight;
+    if (ctx->copy_seq - last > (unsigned long long)mr_context::COPY_RING) last = ctx->copy_seq - mr_context::COPY_RING;
+    MR_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy_ring[last % mr_context::COPY_RING]));
     return MR_OK;
 }
 
@@ -469,7 +484,16 @@ static int ensure_copy_stream(mr_context *ctx)
             MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
             MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rows_done[i], cudaEventDisableTiming));
         }
+        for (auto &e : ctx->ev_copy_ring) MR_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    return MR_OK;
+}
+
+// bookkeeping for mr_wait_copies_until: the copy just queued on the copy stream is number copy_seq
+static int note_copy_queued(mr_context *ctx)
+{
+    MR_CUDA(ctx, cudaEventRecord(ctx->ev_copy_ring[ctx->copy_seq % mr_context::COPY_RING], ctx->copy_stream));
+    ctx->copy_seq++;
     return MR_OK;
 }
 
@@ -552,6 +576,7 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_rows, N * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (out_count) MR_CUDA(ctx, cudaMemcpyAsync(out_count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
         MR_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+        RC(note_copy_queued(ctx));
         ctx->copy_pending[slot] = true;
         ctx->rows_cur = slot ^ 1;
         return MR_OK;
@@ -575,6 +600,7 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         if (*out_count > 0)
             MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_out, (size_t)*out_count * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
         MR_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+        RC(note_copy_queued(ctx));
         ctx->copy_pending[slot] = true;
         ctx->rows_cur = slot ^ 1;
     } else if (out_points && !dev_out && *out_count > 0) {

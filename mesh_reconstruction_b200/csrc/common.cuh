@@ -71,6 +71,9 @@ struct mr_context {
     cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_rows_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
+    static constexpr int COPY_RING = 32;          // completion events of the last row copies (mr_wait_copies_until)
+    cudaEvent_t ev_copy_ring[COPY_RING] = {};
+    unsigned long long copy_seq = 0;              // row copies queued so far by the async / submit calls
     int rows_cur = 0;
     // profiling
     bool profile = false;

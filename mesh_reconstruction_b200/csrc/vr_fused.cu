@@ -20,6 +20,7 @@
 // Thread layout: 42 x 12.  Thread (tx, ty) owns column pair tx (D-local columns 2tx, 2tx+1) of rows
 // 1 + ty + 12k, k = 0..6; the row parity -- hence which column of the pair is red -- is fixed per
 // thread, and every shared-memory address is `base + k * const`.
+#include <cstddef>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -46,9 +47,14 @@ struct Smem {
     alignas(128) uint8_t i0[IH * IPITCH];
     alignas(128) uint8_t i1[IH * IPITCH];
     float Ix[2][PLANE], Iy[2][PLANE], Iz[2][PLANE];        // [colour][row * NP + idx]; colour 0 = red = (x + y) even
-    float du[2][PLANE], dv[2][PLANE], ws[2][PLANE];
+                                                           // (Ix + Iy are reused as float2 diag[2][PLANE] by the SOR sweeps)
+    float2 uv[2][PLANE];                                   // (du, dv) interleaved: one 64-bit access per neighbour
+    float ws[2][PLANE];
     alignas(8) unsigned long long bar;
 };
+
+static_assert(offsetof(Smem, Iy) == offsetof(Smem, Ix) + sizeof(float) * 2 * PLANE && offsetof(Smem, Ix) % 8 == 0,
+              "Ix + Iy must be one contiguous 8-byte aligned block (reused as the float2 diagonal plane)");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,10 +104,8 @@ __device__ __forceinline__ void stage_phases(Smem &s, const int tid, const int d
         for (int k = 0; k < RSLOTS; k++) {
             const int idx = (ty + k * TY) * NP + tx;
             if (FIRST) u[k] = v[k] = make_float2(0.f, 0.f);
-            s.du[pr][idx] = u[k].x;
-            s.du[pr ^ 1][idx] = u[k].y;
-            s.dv[pr][idx] = v[k].x;
-            s.dv[pr ^ 1][idx] = v[k].y;
+            s.uv[pr][idx] = make_float2(u[k].x, v[k].x);
+            s.uv[pr ^ 1][idx] = make_float2(u[k].y, v[k].y);
         }
     }
     if (USE_TMA) {
@@ -139,11 +143,12 @@ __device__ __forceinline__ void stage_phases(Smem &s, const int tid, const int d
                     iz[t] = zc[t];
                 }
                 if (r < DH - 1) {
-                    const float u0 = s.du[pr][idx], u1 = s.du[pr ^ 1][idx], v0 = s.dv[pr][idx], v1 = s.dv[pr ^ 1][idx];
-                    w[0] = vr_smooth_weight(u1 - u0, v1 - v0, s.du[pr ^ 1][idx + NP] - u0, s.dv[pr ^ 1][idx + NP] - v0);
-                    if (tx < NP - 1)
-                        w[1] = vr_smooth_weight(s.du[pr][idx + 1] - u1, s.dv[pr][idx + 1] - v1, s.du[pr][idx + NP] - u1,
-                                                s.dv[pr][idx + NP] - v1);
+                    const float2 p0 = s.uv[pr][idx], p1 = s.uv[pr ^ 1][idx], d0 = s.uv[pr ^ 1][idx + NP];
+                    w[0] = vr_smooth_weight(p1.x - p0.x, p1.y - p0.y, d0.x - p0.x, d0.y - p0.y);
+                    if (tx < NP - 1) {
+                        const float2 r1 = s.uv[pr][idx + 1], d1 = s.uv[pr][idx + NP];
+                        w[1] = vr_smooth_weight(r1.x - p1.x, r1.y - p1.y, d1.x - p1.x, d1.y - p1.y);
+                    }
                 }
             } else {
 #pragma unroll
@@ -160,11 +165,11 @@ __device__ __forceinline__ void stage_phases(Smem &s, const int tid, const int d
                         const int i = py * IPITCH + px;
                         iz[t] = (float)s.i1[i] - (float)s.i0[i];
                         if (r < DH - 1 && c < DW - 1) {
-                            const float uu = s.du[col][idx], vv = s.dv[col][idx];
+                            const float2 pc = s.uv[col][idx];
                             float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
                             const int ir = idx + t, id = idx + NP;
-                            if (x < W - 1) { ux = s.du[o][ir] - uu; vx = s.dv[o][ir] - vv; }
-                            if (y < H - 1) { uy = s.du[o][id] - uu; vy = s.dv[o][id] - vv; }
+                            if (x < W - 1) { const float2 q = s.uv[o][ir]; ux = q.x - pc.x; vx = q.y - pc.y; }
+                            if (y < H - 1) { const float2 q = s.uv[o][id]; uy = q.x - pc.x; vy = q.y - pc.y; }
                             w[t] = vr_smooth_weight(ux, vx, uy, vy);
                         }
                     }
@@ -236,7 +241,8 @@ __device__ __forceinline__ void pair_phases(Smem &s, const int tid, const int dx
                 d.Iyy = iyd - iyu;
                 d.Ixz = izr - izl;
                 d.Iyz = izd - izu;
-                l = vr_data_term(d, s.du[col][idx], s.dv[col][idx]);
+                const float2 pc = s.uv[col][idx];
+                l = vr_data_term(d, pc.x, pc.y);
                 // link weights -> diagonal (colour-dependent accumulation order)
                 float wsP = s.ws[col][idx];
                 float sR = hasR[col] ? wsP : 0.f, sD = hasD ? wsP : 0.f;
@@ -249,6 +255,23 @@ __device__ __forceinline__ void pair_phases(Smem &s, const int tid, const int dx
     }
 
     // ---- red-black SOR ---------------------------------------------------------------------------------------------
+    // The derivative planes are dead from here on: park the diagonals (A11, A22) in their place (own entries only,
+    // one 64-bit load per update) and keep their refined reciprocals in the registers instead.
+    __syncthreads();
+    float2 (*diag)[PLANE] = reinterpret_cast<float2 (*)[PLANE]>(&s.Ix[0][0]);
+#pragma unroll
+    for (int k = 0; k < SLOTS; k++) {
+        const int idx = base + k * TY * NP;
+        if (tact && (1 + ty + k * TY) <= DH - 2) {
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+                diag[col][idx] = make_float2(A11[k][col], A22[k][col]);
+                A11[k][col] = vr_rcp_refined(A11[k][col]);
+                A22[k][col] = vr_rcp_refined(A22[k][col]);
+            }
+        }
+    }
+
     // Half-sweep hs (0 .. 2 * VR_SOR - 1) has to be right on tile + (2 * VR_SOR - 1 - hs) only: D-row r < HALO is
     // needed while hs < r, row r > HALO + OTH - 1 while hs < DH - 1 - r.  (Skipping is as good as updating with
     // stale neighbours: either way the row's values are never read by a pixel that still matters.)
@@ -276,11 +299,12 @@ __device__ __forceinline__ void pair_phases(Smem &s, const int tid, const int dx
                         float wsP = s.ws[col][idx];
                         float sR = hasR[col] ? wsP : 0.f, sD = (INTERIOR || y < H - 1) ? wsP : 0.f;
                         float sL = hasL[col] ? s.ws[o][iL] : 0.f, sU = (INTERIOR || y > 0) ? s.ws[o][iU] : 0.f;
-                        float u = s.du[col][idx], v = s.dv[col][idx];
-                        vr_sor_update(u, v, sL, sR, sU, sD, s.du[o][iL], s.du[o][iR], s.du[o][iU], s.du[o][iD], s.dv[o][iL], s.dv[o][iR],
-                                      s.dv[o][iU], s.dv[o][iD], B1[k][col], B2[k][col], A12[k][col], A11[k][col], A22[k][col]);
-                        s.du[col][idx] = u;
-                        s.dv[col][idx] = v;
+                        float2 p = s.uv[col][idx];
+                        const float2 pL = s.uv[o][iL], pR = s.uv[o][iR], pU = s.uv[o][iU], pD = s.uv[o][iD];
+                        const float2 dg = diag[col][idx];
+                        vr_sor_update_r(p.x, p.y, sL, sR, sU, sD, pL.x, pR.x, pU.x, pD.x, pL.y, pR.y, pU.y, pD.y, B1[k][col], B2[k][col],
+                                        A12[k][col], dg.x, dg.y, A11[k][col], A22[k][col]);
+                        s.uv[col][idx] = p;
                     }
                 }
             }
@@ -344,7 +368,8 @@ __global__ void __launch_bounds__(NT, 1) vr_fused_kernel(const uint8_t *__restri
         if (x < W && y < H) {
             const int r = tyy + HALO;
             const int col = r & 1, idx = r * NP + p + HALO / 2;
-            const float u0 = s.du[col][idx], v0 = s.dv[col][idx], u1 = s.du[col ^ 1][idx], v1 = s.dv[col ^ 1][idx];
+            const float2 q0 = s.uv[col][idx], q1 = s.uv[col ^ 1][idx];
+            const float u0 = q0.x, v0 = q0.y, u1 = q1.x, v1 = q1.y;
             const size_t g = (size_t)y * W + x;
             const bool second = x + 1 < W;
             if (LAST) {

@@ -306,10 +306,15 @@ def test_submit_main_frame_is_async_and_equal():
     cnt = torch.zeros(4, dtype=torch.int32).pin_memory()
     for i in range(4):
         mr.submit_main_frame(r, fpin[i], sc.cameras[i], [fpin[i + 1]], [sc.cameras[i + 1]], out=rows[i], out_count=cnt[i:i + 1])
-    r.ctx.synchronize()
+    # consume in submission order while later frames are still in flight (ring of pinned buffers)
     for i in range(4):
+        r.ctx.wait_copies_until(3 - i)
         assert int(cnt[i]) == len(ref[i])
         assert np.array_equal(rows[i].numpy()[:len(ref[i])], ref[i], equal_nan=True)
+    r.ctx.wait_copies_until(100)                 # more than were ever queued: returns at once
+    with pytest.raises(mr.MeshReconError):
+        r.ctx.wait_copies_until(-1)
+    r.ctx.synchronize()
     drows = torch.empty((W * H, 7), dtype=torch.float32, device="cuda")
     dcnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     fdev = [torch.from_numpy(f).cuda() for f in frames]
