@@ -133,6 +133,13 @@ int mr_process_main_frame_async(mr_context *ctx, const uint8_t *main_frame, cons
 int mr_submit_main_frame(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
                          const uint8_t *const *side_frames, const float *side_cameras, float *out_points,
                          int *out_count);
+/* mr_submit_main_frame can replay its launch sequence as one CUDA graph from the second submission of a given shape
+ * (same n_side / flow method / host-vs-device inputs) on: one front-end launch per main frame instead of ~35, which
+ * keeps the small kernels at full speed while the PCIe link is busy with the previous frame's rows.
+ * mode 0 = never, 1 = when out_points is host memory (default), 2 = always.  Results are identical in every mode.
+ * mr_graph_launch_count: main frames replayed as a graph so far. */
+int mr_set_use_graphs(mr_context *ctx, int mode);
+uint64_t mr_graph_launch_count(const mr_context *ctx);
 /* Block until every outstanding row copy of mr_process_main_frame_async / mr_submit_main_frame has landed. */
 int mr_wait_copies(mr_context *ctx);
 /* Block until at most max_in_flight of the row copies queued so far are still outstanding (they complete in

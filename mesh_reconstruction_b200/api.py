@@ -68,6 +68,9 @@ def load_library():
     L.mr_process_main_frame_async.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, ip]
     L.mr_wait_copies.argtypes = [vp]
     L.mr_wait_copies_until.argtypes = [vp, C.c_int]
+    L.mr_set_use_graphs.argtypes = [vp, C.c_int]
+    L.mr_graph_launch_count.argtypes = [vp]
+    L.mr_graph_launch_count.restype = C.c_uint64
     L.mr_submit_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, vp]
     L.mr_points_device.argtypes = [vp, ip]
     L.mr_points_device.restype = vp
@@ -139,6 +142,14 @@ class Context:
     @property
     def stream(self):
         return self.lib.mr_stream(self.h)
+
+    def set_use_graphs(self, mode):
+        """CUDA-graph replay of ``submit_main_frame``'s launch sequence: 0 never, 1 for host rows (default), 2 always."""
+        self.check(self.lib.mr_set_use_graphs(self.h, int(mode)))
+
+    @property
+    def graph_launches(self):
+        return int(self.lib.mr_graph_launch_count(self.h))
 
     @property
     def launches(self):

@@ -153,6 +153,7 @@ void mr_destroy(mr_context *ctx)
     for (int i = 0; i < 2; i++) if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
     for (int i = 0; i < 2; i++) if (ctx->ev_rows_done[i]) cudaEventDestroy(ctx->ev_rows_done[i]);
     for (auto e : ctx->ev_copy_ring) if (e) cudaEventDestroy(e);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     for (auto &r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -213,10 +214,21 @@ int mr_set_vr_impl(int impl)
     return MR_OK;
 }
 
+int mr_set_use_graphs(mr_context *ctx, int on)
+{
+    CHECK_CTX(ctx);
+    CHECK_ARG(ctx, on >= 0 && on <= 2, "mode must be 0 (never), 1 (host rows) or 2 (always)");
+    ctx->graphs_mode = on;
+    return MR_OK;
+}
+
+uint64_t mr_graph_launch_count(const mr_context *ctx) { return ctx ? ctx->graph_launches : 0; }
+
 int mr_load_mesh(mr_context *ctx, const float *vertices_xyzw, int n_vertices, const int32_t *faces, int n_faces)
 {
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
+    ctx->graph_warm = false;   // per-face buffers may grow: the next submission runs plainly (and allocates) again
     CHECK_ARG(ctx, n_vertices >= 0 && n_faces >= 0, "negative count");
     CHECK_ARG(ctx, n_faces == 0 || (vertices_xyzw && faces), "null mesh pointers");
     if (n_faces == 0) return k_load_mesh(ctx, nullptr, nullptr, 0);
@@ -510,16 +522,12 @@ static void *device_alias(const void *p)
     return nullptr;
 }
 
-static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
-                                   const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count,
-                                   int mode)
+// Enqueues steps recon.cpp:70-89 (depth, then projected -> mixBackground -> calculateFlow per side camera) on the
+// context stream.  Device work only -- no allocation after the first call of a given shape, no synchronisation --
+// so the sequence can be stream-captured into a CUDA graph by mr_submit_main_frame.
+static int enqueue_flows(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                         const uint8_t *const *side_frames, const float *side_cameras, const float **d_flows, float **depth_out)
 {
-    CHECK_CTX(ctx);
-    SET_DEVICE(ctx);
-    const bool async_copy = mode == PMF_ASYNC_COPY;
-    CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && (out_count || mode == PMF_SUBMIT), "null argument");
-    CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
-    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
     size_t N = ctx->N;
     const uint8_t *d_main = (const uint8_t *)mr_in(ctx, main_frame, N, "in_main");
     unsigned long long *vis_main = mr_buf<unsigned long long>(ctx, "vis_main", N);
@@ -531,9 +539,7 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         RC(k_raster(ctx, Pm, vis_main));            // recon.cpp:70  depth = render->depth(camera(fa))
         RC(k_resolve_depth(ctx, vis_main, depth));
     }
-    const float *d_flows[MR_MAX_SIDE];
     for (int i = 0; i < n_side; i++) {           // recon.cpp:81
-        CHECK_ARG(ctx, side_frames[i], "null side frame");
         const uint8_t *d_side = (const uint8_t *)mr_in(ctx, side_frames[i], N, "in_side");
         float *flow = mr_buf<float>(ctx, flow_name(i), N * 4);
         uint8_t *mixed = mr_buf<uint8_t>(ctx, mixed_name(i), N);
@@ -548,30 +554,128 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         RC(calculate_flow_dev(ctx, d_main, mixed, flow, ctx->use_farneback));                        // recon.cpp:89
         d_flows[i] = flow;
     }
+    *depth_out = depth;
+    return MR_OK;
+}
+
+static bool is_pinned_or_device(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeHost;
+}
+
+// mr_submit_main_frame: the whole device sequence of one main frame (~35 launches at S = 1).  After a first plain
+// run of a given shape (which allocates every buffer), later submissions are stream-captured and replayed as ONE
+// CUDA graph (cudaGraphExecUpdate re-targets the pointers and per-camera constants of the instantiated graph):
+// the front end then fetches a single launch instead of ~35 command packets over PCIe.  That matters exactly when
+// the link is busy with the previous frame's 58 MB row DMA -- measured: stream launches slow the small kernels at
+// the head of a frame by up to 2x under that traffic, graph launches do not (scripts/graph_contention_micro.py,
+// scripts/dma_contention_probe.py).
+static int submit_enqueue(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                          const uint8_t *const *side_frames, const float *side_cameras, float *d_rows, int *d_cnt, bool host_rows)
+{
+    // shape of the launch sequence: anything that changes the graph's topology
+    unsigned long long key = (unsigned long long)n_side | ((unsigned long long)ctx->use_farneback << 8) | ((unsigned long long)(g_mr_vr_impl & 0xff) << 9) |
+                             ((unsigned long long)(g_mr_vr_tma & 1) << 17) | ((unsigned long long)(mr_is_device_ptr(main_frame) ? 1 : 0) << 18);
+    // Graph replay is used when the rows go to the HOST (graphs_mode 1, the default) or always (2).  With rows left in
+    // HBM there is no PCIe traffic to hide from, and with two contexts per GPU plain stream launches interleave the
+    // two frames' kernels slightly better (measured at 1080p, 2 contexts: 1.24 vs 1.27 ms/pair resident, but
+    // 1.38 vs 1.30 ms/pair with host rows).
+    bool capturable = (ctx->graphs_mode == 2 || (ctx->graphs_mode == 1 && host_rows)) && !ctx->profile && is_pinned_or_device(main_frame);
+    for (int i = 0; i < n_side; i++) {
+        key |= (unsigned long long)(mr_is_device_ptr(side_frames[i]) ? 1 : 0) << (19 + i);
+        capturable = capturable && is_pinned_or_device(side_frames[i]);
+    }
+    const float *d_flows[MR_MAX_SIDE];
+    float *depth = nullptr;
+    if (!capturable || !ctx->graph_warm || ctx->graph_key != key) {
+        RC(enqueue_flows(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_flows, &depth));
+        RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_rows, nullptr, d_cnt));
+        if (capturable) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            ctx->graph_warm = true;
+            ctx->graph_key = key;
+        }
+        return MR_OK;
+    }
+    const uint64_t launches0 = ctx->launches;
+    MR_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    int rc = enqueue_flows(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_flows, &depth);
+    if (rc == MR_OK) rc = k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_rows, nullptr, d_cnt);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc != MR_OK || ce != cudaSuccess || !g) {
+        // capture refused something: drop graphs for this context and run the frame the plain way
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        ctx->graphs_mode = 0;
+        ctx->launches = launches0;
+        RC(enqueue_flows(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_flows, &depth));
+        return k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_rows, nullptr, d_cnt);
+    }
+    if (ctx->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(ctx->graph_exec, g, &info) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphExecDestroy(ctx->graph_exec);
+            ctx->graph_exec = nullptr;
+        }
+    }
+    if (!ctx->graph_exec) {
+        ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+        if (ce != cudaSuccess) {
+            cudaGraphDestroy(g);
+            return mr_fail(ctx, MR_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(ce));
+        }
+    }
+    cudaGraphDestroy(g);
+    MR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    ctx->graph_launches++;
+    return MR_OK;
+}
+
+static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, const float main_camera[16], int n_side,
+                                   const uint8_t *const *side_frames, const float *side_cameras, float *out_points, int *out_count,
+                                   int mode)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    const bool async_copy = mode == PMF_ASYNC_COPY;
+    CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && (out_count || mode == PMF_SUBMIT), "null argument");
+    CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
+    for (int i = 0; i < n_side; i++) CHECK_ARG(ctx, side_frames[i], "null side frame");
+    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
+    size_t N = ctx->N;
     bool dev_out = out_points && mr_is_device_ptr(out_points);
     if (mode == PMF_SUBMIT) {
-        // fully asynchronous: nothing below waits for the GPU; rows and count are delivered by device-side stores
+        // fully asynchronous: nothing below waits for the GPU; rows and count are delivered by device-side stores / DMA
         CHECK_ARG(ctx, out_points, "mr_submit_main_frame needs an output buffer");
         float *out_alias = (float *)device_alias(out_points);
         int *cnt_alias = out_count ? (int *)device_alias(out_count) : nullptr;
         CHECK_ARG(ctx, out_alias && (!out_count || cnt_alias), "mr_submit_main_frame: out_points / out_count must be device or pinned host memory");
         CHECK_ARG(ctx, !out_count || mr_is_device_ptr(out_points) == mr_is_device_ptr(out_count), "mr_submit_main_frame: out_points and out_count must live in the same memory space");
         RC(ensure_copy_stream(ctx));
+        ctx->last_S = n_side;
         if (dev_out) {
-            int *d_cnt = (cnt_alias && mr_is_device_ptr(out_count)) ? cnt_alias : mr_buf<int>(ctx, "count", 1);
-            RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, out_points, nullptr, cnt_alias ? cnt_alias : d_cnt));
-            return MR_OK;
+            int *d_cnt = cnt_alias ? cnt_alias : mr_buf<int>(ctx, "count", 1);
+            if (!d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_submit_main_frame", "alloc");
+            return submit_enqueue(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, d_cnt, false);
         }
         const int slot = ctx->rows_cur;
         float *d_rows = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
         int *d_cnt = mr_buf<int>(ctx, slot ? "count1" : "count0", 1);
         if (!d_rows || !d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_submit_main_frame", "alloc");
+        // this slot's previous rows (two submissions ago) must have left for the host before they are overwritten
         if (ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
-        RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_rows, nullptr, d_cnt));
+        RC(submit_enqueue(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_rows, d_cnt, true));
         MR_CUDA(ctx, cudaEventRecord(ctx->ev_rows_done[slot], ctx->stream));
         MR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows_done[slot], 0));
         // DMA (copy engine, no SMs) of the row buffer at full capacity -- the row count is not known on the host without
-        // a synchronisation, and a device-side copy kernel over PCIe measured only ~24 GB/s against ~52 GB/s for the
+        // a synchronisation, and a device-side copy kernel over PCIe measured only ~24 GB/s against ~57 GB/s for the
         // DMA; only the first *out_count rows are meaningful.  58 MB at 1080p: hidden under the next frame's compute.
         MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_rows, N * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (out_count) MR_CUDA(ctx, cudaMemcpyAsync(out_count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -581,6 +685,9 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         ctx->rows_cur = slot ^ 1;
         return MR_OK;
     }
+    const float *d_flows[MR_MAX_SIDE];
+    float *depth = nullptr;
+    RC(enqueue_flows(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_flows, &depth));
     const bool pipelined = async_copy && out_points && !dev_out;
     float *d_out;
     int slot = 0;

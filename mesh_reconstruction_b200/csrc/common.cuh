@@ -75,6 +75,12 @@ struct mr_context {
     cudaEvent_t ev_copy_ring[COPY_RING] = {};
     unsigned long long copy_seq = 0;              // row copies queued so far by the async / submit calls
     int rows_cur = 0;
+    // mr_submit_main_frame: the per-frame launch sequence replayed as one CUDA graph (api.cu: submit_enqueue)
+    int graphs_mode = 1;                          // mr_set_use_graphs: 0 never, 1 when the rows go to the host, 2 always; zeroed if a capture is ever refused
+    bool graph_warm = false;                      // a plain run of shape graph_key has allocated every buffer
+    unsigned long long graph_key = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_launches = 0;
     // profiling
     bool profile = false;
     std::vector<ProfRec> prof_pending;

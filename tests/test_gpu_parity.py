@@ -311,6 +311,7 @@ def test_submit_main_frame_is_async_and_equal():
         r.ctx.wait_copies_until(3 - i)
         assert int(cnt[i]) == len(ref[i])
         assert np.array_equal(rows[i].numpy()[:len(ref[i])], ref[i], equal_nan=True)
+    assert r.ctx.graph_launches == 3             # first submission plain (allocates), the next three as one CUDA graph each
     r.ctx.wait_copies_until(100)                 # more than were ever queued: returns at once
     with pytest.raises(mr.MeshReconError):
         r.ctx.wait_copies_until(-1)
@@ -323,6 +324,26 @@ def test_submit_main_frame_is_async_and_equal():
     assert int(dcnt.item()) == len(ref[2]) and np.array_equal(drows.cpu().numpy()[:len(ref[2])], ref[2], equal_nan=True)
     with pytest.raises(mr.MeshReconError):       # pageable host output cannot be written asynchronously
         mr.submit_main_frame(r, frames[0], sc.cameras[0], [frames[1]], [sc.cameras[1]], out=np.empty((W * H, 7), f32))
+    # graph replay re-targets pointers and camera constants: different frames / cameras / shapes through the same exec
+    r.ctx.set_use_graphs(2)                      # also for device rows (default: host rows only)
+    mr.submit_main_frame(r, fdev[2], sc.cameras[2], [fdev[3]], [sc.cameras[3]], out=drows, out_count=dcnt)   # plain run of the new shape
+    n0 = r.ctx.graph_launches
+    for i in (3, 0, 1):
+        mr.submit_main_frame(r, fdev[i], sc.cameras[i], [fdev[i + 1]], [sc.cameras[i + 1]], out=drows, out_count=dcnt)
+        r.ctx.synchronize()
+        assert int(dcnt.item()) == len(ref[i]) and np.array_equal(drows.cpu().numpy()[:len(ref[i])], ref[i], equal_nan=True)
+    assert r.ctx.graph_launches == n0 + 3
+    ref2 = mr.process_main_frame(r, frames[0], sc.cameras[0], [frames[1], frames[2]], [sc.cameras[1], sc.cameras[2]]).copy()
+    for _ in range(2):                           # S = 2: new shape -> one plain run, then a re-instantiated graph
+        mr.submit_main_frame(r, fdev[0], sc.cameras[0], [fdev[1], fdev[2]], [sc.cameras[1], sc.cameras[2]], out=drows, out_count=dcnt)
+        r.ctx.synchronize()
+        assert int(dcnt.item()) == len(ref2) and np.array_equal(drows.cpu().numpy()[:len(ref2)], ref2, equal_nan=True)
+    assert r.ctx.graph_launches == n0 + 4
+    r.ctx.set_use_graphs(0)
+    mr.submit_main_frame(r, fdev[2], sc.cameras[2], [fdev[3]], [sc.cameras[3]], out=drows, out_count=dcnt)
+    r.ctx.synchronize()
+    assert r.ctx.graph_launches == n0 + 4
+    assert int(dcnt.item()) == len(ref[2]) and np.array_equal(drows.cpu().numpy()[:len(ref[2])], ref[2], equal_nan=True)
 
 
 def test_device_pointers_in_and_out():
