@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--mesh-err", type=float, default=0.02)
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame pairs timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--vr-impl", type=int, default=None)
-    ap.add_argument("--contexts", type=int, default=2, help="library contexts (streams) per GPU; main frames alternate between them so that "
+    ap.add_argument("--contexts", type=int, default=3, help="library contexts (streams) per GPU; main frames alternate between them so that "
                     "one pair's kernel tails / low-occupancy phases overlap the other's (measured +15 %% at 2)")
     ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
     args = ap.parse_args()
