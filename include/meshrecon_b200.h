@@ -28,6 +28,7 @@
 #ifndef MESHRECON_B200_H
 #define MESHRECON_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,18 @@ int mr_wait_copies(mr_context *ctx);
  * buffer -- or with the number of frames queued since the results one wants to read -- lets the host consume one
  * main frame's rows while the following ones are still being computed and copied.  0 == mr_wait_copies. */
 int mr_wait_copies_until(mr_context *ctx, int max_in_flight);
+/* The path's one exchange step when main frames are sharded over GPUs, one rank per GPU (the reference is
+ * single-process and appends every main frame's rows, recon.cpp:115-116): variable-length all-gather of point rows
+ * over an NCCL communicator created by the host (nccl_comm is its ncclComm_t).  rows: this rank's `count` rows
+ * (count x 7 floats, device memory).  out_rows (device, capacity out_capacity_rows rows -- at least the gathered
+ * total on every rank) receives the rows of all ranks concatenated in RANK ORDER, which with contiguous blocks of
+ * main frames per rank is the reference's append order; out_counts[world] / out_total (host, may be NULL) the
+ * per-rank counts and their sum.  One 4-byte all-gather of the counts (one stream synchronisation), then one
+ * grouped NCCL operation of per-rank broadcasts with the exact counts (no padding), enqueued on mr_stream(ctx):
+ * out_rows is complete after mr_synchronize().  NCCL is resolved at run time from the host process (or
+ * libnccl.so.2); MR_ENODEVICE if it cannot be found. */
+int mr_allgather_points(mr_context *ctx, void *nccl_comm, const float *rows, int count, float *out_rows,
+                        size_t out_capacity_rows, int *out_counts, int *out_total);
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */
 const float *mr_points_device(mr_context *ctx, int *out_count);

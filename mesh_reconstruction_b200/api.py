@@ -69,6 +69,7 @@ def load_library():
     L.mr_wait_copies.argtypes = [vp]
     L.mr_wait_copies_until.argtypes = [vp, C.c_int]
     L.mr_set_use_graphs.argtypes = [vp, C.c_int]
+    L.mr_allgather_points.argtypes = [vp, vp, vp, C.c_int, vp, C.c_size_t, ip, ip]
     L.mr_graph_launch_count.argtypes = [vp]
     L.mr_graph_launch_count.restype = C.c_uint64
     L.mr_submit_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, vp]

@@ -61,6 +61,8 @@ struct mr_context {
     int last_S = 0;
     // pinned host scratch for small readbacks
     int *h_count = nullptr;
+    int *h_xchg = nullptr;                        // pinned per-rank counts of mr_allgather_points (exchange.cu)
+    int h_xchg_cap = 0;
     // pyramid geometry of compare()
     int n_levels = 0;
     int lw[MR_MAX_LEVELS], lh[MR_MAX_LEVELS];

@@ -43,3 +43,73 @@ def allgather_points(rows, count=None, group=None):
     recv = recv.view(world, mx, rows.shape[1])
     out = torch.cat([recv[r, :counts_h[r]] for r in range(world)], 0)
     return out, counts_h
+
+
+# ---- the same exchange through the C ABI (mr_allgather_points) -------------------------------------------
+# A C/C++ host creates its ncclComm_t itself; from Python the helpers below build one with the NCCL copy that is
+# already mapped into the process (torch's), using torch.distributed only to pass the 128-byte unique id around.
+
+def _nccl_lib():
+    import ctypes as C
+    path = "libnccl.so.2"
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl.so" in line:
+                    path = line.split()[-1]
+                    break
+    except OSError:
+        pass
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)   # global: libmeshrecon_b200.so resolves NCCL from the process first
+
+
+def raw_nccl_comm(device, group=None):
+    """ncclComm_t (as an int) spanning the ranks of `group`, for mr_allgather_points.  Collective."""
+    import ctypes as C
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+
+    nccl = _nccl_lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = UniqueId()
+    if rank == 0:
+        rc = nccl.ncclGetUniqueId(C.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+    box = [C.string_at(C.byref(uid), 128) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    C.memmove(C.byref(uid), box[0], 128)
+    torch.cuda.set_device(device)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    rc = nccl.ncclCommInitRank(C.byref(comm), world, uid, rank)
+    if rc != 0:
+        raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+    return comm.value
+
+
+def destroy_raw_nccl_comm(comm):
+    import ctypes as C
+    nccl = _nccl_lib()
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    nccl.ncclCommDestroy(C.c_void_p(comm))
+
+
+def allgather_points_cabi(ctx, comm, rows, count, out=None):
+    """Variable-length all-gather of CUDA point rows through ``mr_allgather_points`` (exact counts, rank-order
+    concatenation).  ctx: api.Context of this rank's GPU; comm: raw ncclComm_t.  Returns (all_rows, counts)."""
+    import ctypes as C
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    counts = (C.c_int * max(world, 1))()
+    total = C.c_int(0)
+    if out is None:
+        cap = torch.tensor([int(count)], dtype=torch.int64, device=rows.device)
+        if world > 1:
+            dist.all_reduce(cap)                      # capacity = exact total (one tiny collective; a C host sizes for the worst case)
+        out = torch.empty((max(int(cap.item()), 1), 7), dtype=torch.float32, device=rows.device)
+    ctx.check(ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), C.c_void_p(rows.data_ptr()), int(count), C.c_void_p(out.data_ptr()),
+                                          out.shape[0], counts, C.byref(total)))
+    ctx.synchronize()
+    return out[:total.value], [int(c) for c in counts][:world]

@@ -1,0 +1,85 @@
+"""mr_allgather_points (C ABI, NCCL): the path's one exchange step.
+
+* world = 1 communicator in-process: runs on the single-GPU tier (plumbing: run-time NCCL resolution, counts, offsets);
+* world = 2 through torch.distributed.run, one rank per GPU: skipped with fewer than two GPUs.  The checker is
+  shard.allgather_points (torch.distributed), itself covered on CPU with gloo in test_shard_gloo.py.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import mesh_reconstruction_b200 as mr
+from mesh_reconstruction_b200 import shard
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = mr.api.Context(64, 48, local)
+comm = shard.raw_nccl_comm(local)
+g = torch.Generator().manual_seed(100 + rank)
+for trial, count in enumerate([1000 + 37 * rank, 0 if rank == 0 else 5, 123456 * (rank + 1)]):
+    rows = torch.rand((count + 3, 7), generator=g).cuda()          # capacity > count: only the first `count` rows travel
+    got, counts = shard.allgather_points_cabi(ctx, comm, rows, count)
+    ref, ref_counts = shard.allgather_points(rows, count)
+    assert counts == ref_counts, (counts, ref_counts)
+    assert got.shape == ref.shape and torch.equal(got, ref), trial
+# an output buffer that is too small is refused (every rank sees the same total, so every rank refuses)
+import ctypes as C
+small = torch.empty((1, 7), device="cuda")
+rc = ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), C.c_void_p(rows.data_ptr()), 10, C.c_void_p(small.data_ptr()), 1, None, None)
+assert rc == -1, rc
+dist.barrier()
+shard.destroy_raw_nccl_comm(comm)
+dist.destroy_process_group()
+print("RANK", rank, "OK")
+"""
+
+
+def _run(world):
+    script = os.path.join(ROOT, "tests", "_exchange_worker_tmp.py")
+    with open(script, "w") as f:
+        f.write(WORKER.format(root=ROOT))
+    try:
+        port = 29600 + (os.getpid() % 300)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), script]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+        for r in range(world):
+            assert f"RANK {r} OK" in p.stdout
+    finally:
+        os.remove(script)
+
+
+def test_allgather_points_cabi_world1():
+    _run(1)
+
+
+def test_allgather_points_cabi_world2():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2)
+
+
+def test_allgather_points_argument_errors():
+    import ctypes as C
+    import torch
+    import mesh_reconstruction_b200 as mr
+    ctx = mr.api.Context(64, 48)
+    rows = torch.zeros((4, 7), device="cuda")
+    host = np.zeros((4, 7), np.float32)
+    assert ctx.lib.mr_allgather_points(ctx.h, None, C.c_void_p(rows.data_ptr()), 4, C.c_void_p(rows.data_ptr()), 4, None, None) == -1   # no communicator
+    assert ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(1), host.ctypes.data_as(C.c_void_p), 4, C.c_void_p(rows.data_ptr()), 4, None, None) == -1   # host rows
+    assert b"device memory" in ctx.lib.mr_last_error(ctx.h)
