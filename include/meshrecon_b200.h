@@ -137,7 +137,7 @@ int mr_submit_main_frame(mr_context *ctx, const uint8_t *main_frame, const float
 /* mr_submit_main_frame can replay its launch sequence as one CUDA graph from the second submission of a given shape
  * (same n_side / flow method / host-vs-device inputs) on: one front-end launch per main frame instead of ~35, which
  * keeps the small kernels at full speed while the PCIe link is busy with the previous frame's rows.
- * mode 0 = never, 1 = when out_points is host memory (default), 2 = always.  Results are identical in every mode.
+ * mode 0 = never, 1 = when out_points is host memory or the Farneback branch is selected (default), 2 = always.  Results are identical in every mode.
  * mr_graph_launch_count: main frames replayed as a graph so far. */
 int mr_set_use_graphs(mr_context *ctx, int mode);
 uint64_t mr_graph_launch_count(const mr_context *ctx);

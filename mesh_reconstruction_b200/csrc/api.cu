@@ -586,7 +586,8 @@ static int submit_enqueue(mr_context *ctx, const uint8_t *main_frame, const floa
     // HBM there is no PCIe traffic to hide from, and with two contexts per GPU plain stream launches interleave the
     // two frames' kernels slightly better (measured at 1080p, 2 contexts: 1.24 vs 1.27 ms/pair resident, but
     // 1.38 vs 1.30 ms/pair with host rows).
-    bool capturable = (ctx->graphs_mode == 2 || (ctx->graphs_mode == 1 && host_rows)) && !ctx->profile && is_pinned_or_device(main_frame);
+    // The Farneback branch (-f) is ~360 short launches per pair: always worth a graph.
+    bool capturable = (ctx->graphs_mode == 2 || (ctx->graphs_mode == 1 && (host_rows || ctx->use_farneback))) && !ctx->profile && is_pinned_or_device(main_frame);
     for (int i = 0; i < n_side; i++) {
         key |= (unsigned long long)(mr_is_device_ptr(side_frames[i]) ? 1 : 0) << (19 + i);
         capturable = capturable && is_pinned_or_device(side_frames[i]);
