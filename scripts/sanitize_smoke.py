@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import mesh_reconstruction_b200 as mr
 from mesh_reconstruction_b200 import synth
-for (W, H, S) in [(160, 128, 2), (101, 67, 1)]:
+for (W, H, S) in [(224, 208, 2), (101, 67, 1)]:   # 224x208: border AND interior VR tiles (TMA path); 101x67: plain loads
     sc = synth.make_scene(W, H, S + 1, step=0.15, mesh_err=0.03, mesh_res=6)
     frames = sc.frames()
     r = mr.Render(W, H, ctx=mr.api.Context(W, H)); r.loadMesh(sc.vertices, sc.faces)
@@ -12,3 +12,17 @@ for (W, H, S) in [(160, 128, 2), (101, 67, 1)]:
     fl = mr.calculateFlow(frames[0], frames[1], useFarneback=True)
     q = r.depthSamples(sc.cameras[:1], np.array([[3, 5]]), np.array([[7, 9]]))
     print(W, H, S, tri.shape, float(np.abs(fl).max()), q)
+
+# submit path: plain first run, then CUDA-graph replays, rows by DMA into pinned buffers
+import torch
+W, H = 224, 208
+sc = synth.make_scene(W, H, 4, step=0.15, mesh_err=0.03, mesh_res=6)
+frames = [torch.from_numpy(f).pin_memory() for f in sc.frames()]
+r = mr.Render(W, H, ctx=mr.api.Context(W, H)); r.loadMesh(sc.vertices, sc.faces)
+rows = [torch.empty((W * H, 7), dtype=torch.float32).pin_memory() for _ in range(3)]
+cnt = torch.zeros(3, dtype=torch.int32).pin_memory()
+for i in range(3):
+    mr.submit_main_frame(r, frames[i], sc.cameras[i], [frames[i + 1]], [sc.cameras[i + 1]], out=rows[i], out_count=cnt[i:i + 1])
+r.ctx.wait_copies_until(0)
+r.ctx.synchronize()
+print("submit", cnt.tolist(), r.ctx.graph_launches)
