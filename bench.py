@@ -148,6 +148,11 @@ def main():
     ap.add_argument("--vr-impl", type=int, default=None)
     ap.add_argument("--contexts", type=int, default=3, help="library contexts (streams) per GPU; main frames alternate between them so that "
                     "one pair's kernel tails / low-occupancy phases overlap the other's (measured +15 %% at 2)")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the point rows reach every rank -- p2p: copy-engine pushes into the peers' buffers over NVLink "
+                         "(CUDA IPC, no SMs); nccl: all_gather_into_tensor")
+    ap.add_argument("--graphs", type=int, default=None, choices=[0, 1, 2],
+                    help="mr_set_use_graphs mode (default: the library's: graph replay when rows go to the host or with --farneback)")
     ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -188,6 +193,8 @@ def main():
         r_.loadMesh(scene.vertices, scene.faces)
         if args.farneback:
             lib.mr_set_use_farneback(r_.ctx.h, 1)
+        if args.graphs is not None:
+            r_.ctx.set_use_graphs(args.graphs)
     render, ctx = renders[0], renders[0].ctx
     lib_streams = [torch.cuda.ExternalStream(r_.ctx.stream, device=dev) for r_ in renders]
     lib_stream = lib_streams[0]
@@ -198,16 +205,31 @@ def main():
             lib_stream.wait_stream(st)
 
     nbuf = 2 if world > 1 else 1
-    rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
+    use_p2p = world > 1 and args.exchange == "p2p"
+    xch = None
+    if use_p2p:
+        # kernel-free exchange: per buffer set, every rank owns a receive buffer with one slot per rank (rows of B pairs at
+        # full capacity, then the B counts), mapped into every peer over CUDA IPC; the normals kernel writes this rank's rows
+        # straight into its own slot, which is then DMA'd into the same slot of every peer (mr_xchg_push)
+        from mesh_reconstruction_b200.shard import PeerExchange
+        rows_bytes = (B * N * 28 + 255) // 256 * 256
+        xch = [PeerExchange(ctx, rows_bytes + B * 4, dev) for _ in range(nbuf)]
+        rows_dev = [x.slot(rank, (B, N, 7)) for x in xch]
+        counts_dev = [x.slot(rank, (B,), torch.int32, offset_bytes=rows_bytes) for x in xch]
+        for c_ in counts_dev:
+            c_.zero_()
+        xflag = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    else:
+        rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
+        counts_dev = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(nbuf)]
     # every pair of a step lands on the host; two alternating sets so that the host reads step s-1 while step s runs
     rows_pin = [[torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(B)] for _ in range(2)]
     counts_pin = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)]
     per_ctx = [len(range(c, B, nctx)) for c in range(nctx)]     # pairs each context gets per step
     counts = torch.zeros(B, dtype=torch.int64)
     rows_flat = [r.view(B * N, 7) for r in rows_dev]
-    gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 else None
-    gather_counts = [torch.empty((world * B,), dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
-    counts_dev = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 and not use_p2p else None
+    gather_counts = [torch.empty((world * B,), dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 and not use_p2p else None
     pending = [None] * nbuf
 
     def pair(j):                      # j-th pair of this rank, cycling inside its block
@@ -234,12 +256,20 @@ def main():
                                  out=rows_dev[k][b], out_count=counts_dev[k][b:b + 1])
         if world > 1:
             join_streams()
-            # the path's one exchange step: point rows + counts -> every rank over NCCL/NVLink, ASYNC so that it
-            # overlaps the next step's compute (double-buffered send/receive buffers, stream-ordered after this step's kernels)
-            torch.cuda.current_stream().wait_stream(lib_stream)
-            h1 = dist.all_gather_into_tensor(gather_counts[k], counts_dev[k], async_op=True)
-            h2 = dist.all_gather_into_tensor(gather_rows[k], rows_flat[k], async_op=True)
-            pending[k] = (h1, h2)
+            if use_p2p:
+                # the path's one exchange step without kernels: this rank's slot (rows + counts of the step) is DMA'd
+                # into every peer's buffer over NVLink, stream-ordered after this step's kernels; a 4-byte all-reduce entered
+                # after the pushes is the completion signal (when it is done everywhere, every slot of set k has landed)
+                xch[k].push()
+                with torch.cuda.stream(xch[k].signal_stream()):
+                    pending[k] = (dist.all_reduce(xflag[k], async_op=True),)
+            else:
+                # NCCL all-gather of rows + counts, ASYNC so that it overlaps the next step's compute (double-buffered send /
+                # receive buffers, stream-ordered after this step's kernels)
+                torch.cuda.current_stream().wait_stream(lib_stream)
+                h1 = dist.all_gather_into_tensor(gather_counts[k], counts_dev[k], async_op=True)
+                h2 = dist.all_gather_into_tensor(gather_rows[k], rows_flat[k], async_op=True)
+                pending[k] = (h1, h2)
 
     def step_e2e(s):
         # host frames in (pinned; H2D inside the call), every pair's point rows + count out to pinned host memory by the
@@ -265,6 +295,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    diag = {}
+
     def timed(fn, steps, first, drain=None):
         for k in range(nbuf):
             wait_pending(k)
@@ -272,8 +304,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = sum(r_.ctx.launches for r_ in renders)
         e0.record(lib_stream)
+        t_host = time.perf_counter()
         for s in range(steps):
             fn(first + s)
+        diag["host_ms_per_step"] = (time.perf_counter() - t_host) * 1e3 / steps     # CPU time to queue a step
         if drain is not None:
             drain()
         if world > 1:
@@ -284,9 +318,12 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms, diag["host_ms_per_step"]], dtype=torch.float64, device=dev)
+            allt = torch.empty((world, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            diag["ms_by_rank"] = [round(float(v) / steps, 3) for v in allt[:, 0]]
+            diag["host_ms_by_rank"] = [round(float(v), 3) for v in allt[:, 1]]
+            ms = float(allt[:, 0].max())
         return ms, sum(r_.ctx.launches for r_ in renders) - l0
 
     # ---- warm-up, then the timed regions ---------------------------------------------------
@@ -295,6 +332,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_res, launches = timed(step_resident, K, Wm)
+    diag_res = dict(diag)
     sampler.stop_flag = True
     for s in range(max(Wm - 2, 1)):
         step_e2e(s)
@@ -316,6 +354,17 @@ def main():
     lib.mr_profile_enable(ctx.h, 0)
     prof_pairs = 2 * B
     stages = {lib.mr_stage_name(i).decode(): {"ms_per_pair": msb[i] / prof_pairs, "launches_per_pair": lb[i] / prof_pairs} for i in range(ns)}
+    if world > 1:
+        # per-rank health for the scaling runs: kernel time per pair (one context, no overlap), SM clock under load
+        cs = sampler.summary()
+        mine = torch.tensor([sum(v["ms_per_pair"] for v in stages.values()), float(cs.get("sm_mhz") or 0), float(cs.get("sm_min_mhz") or 0),
+                             float(sampler.reasons)], dtype=torch.float64, device=dev)
+        allh = torch.empty((world, 4), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        diag_res["kernel_ms_per_pair_by_rank"] = [round(float(v), 4) for v in allh[:, 0]]
+        diag_res["sm_mhz_by_rank"] = [int(v) for v in allh[:, 1]]
+        diag_res["sm_min_mhz_by_rank"] = [int(v) for v in allh[:, 2]]
+        diag_res["clock_reason_bits_by_rank"] = [int(v) for v in allh[:, 3]]
     dom = max(stages, key=lambda k: stages[k]["ms_per_pair"])
     peak, peak_src = load_peaks()
     dom_ms_launch = stages[dom]["ms_per_pair"] / max(stages[dom]["launches_per_pair"], 1)
@@ -355,7 +404,9 @@ def main():
             "config": {"workload": f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S=1 (BASELINE config 4)",
                        "pairs_per_step_per_gpu": B, "contexts_per_gpu": nctx, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
                        "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
-                       "exchange": "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step" if world > 1 else "none (single GPU)"},
+                       "exchange": ("none (single GPU)" if world == 1 else
+                                    "copy-engine pushes of rows + counts into every peer's buffer over NVLink (CUDA IPC, mr_xchg_push; no SMs), overlapped with the next step" if use_p2p else
+                                    "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step")},
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": (N * 28 + 4) * B,   # the DMA moves the full row capacity (count unknown on the host without a sync)
                     "rows_bytes_per_step": int(m_mean * 28 * B),
                     "ms_per_step": ms_e2e / K},
@@ -368,11 +419,24 @@ def main():
                               "frac": path_ach / peak},
             "stages_ms_per_pair": {k: round(v["ms_per_pair"], 4) for k, v in stages.items()},
             "clocks": sampler.summary(),
+            "diag": diag_res,      # host time to queue a step; per-rank device time per step (value uses the max)
         }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        if use_p2p:
+            # every rank must hold every rank's counts of the last steps (exchange sanity, outside the timed regions)
+            for r_ in renders:
+                r_.ctx.synchronize()
+            torch.cuda.synchronize()
+            dist.barrier()
+            for x in xch:
+                got = torch.stack([x.slot(p, (B,), torch.int32, offset_bytes=rows_bytes) for p in range(world)])
+                if int(got.min()) <= 0:
+                    raise SystemExit(f"bench.py: rank {rank} is missing exchanged counts: {got.tolist()}")
+            for x in xch:
+                x.close()
         dist.destroy_process_group()
 
 

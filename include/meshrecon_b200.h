@@ -160,6 +160,22 @@ int mr_wait_copies_until(mr_context *ctx, int max_in_flight);
  * libnccl.so.2); MR_ENODEVICE if it cannot be found. */
 int mr_allgather_points(mr_context *ctx, void *nccl_comm, const float *rows, int count, float *out_rows,
                         size_t out_capacity_rows, int *out_counts, int *out_total);
+/* The same exchange WITHOUT kernels, for one process per GPU on an NVLink / NVSwitch node: every rank allocates a
+ * receive buffer with one slot per rank (mr_xchg_alloc returns the device pointer and its 64-byte CUDA IPC handle),
+ * the host passes the handles around (MPI, torch.distributed, a pipe ...), every rank maps its peers' buffers
+ * (mr_xchg_open) and, per batch of main frames, DMAs its rows into its slot of every peer's buffer with mr_xchg_push:
+ * copy-engine traffic over NVLink, ordered after the work queued so far on mr_stream(ctx), running on
+ * mr_xchg_stream(ctx).  No SMs are used, so the exchange cannot slow the path's kernels down (a kernel-based
+ * collective takes SMs from the 1-CTA-per-SM variational-refinement kernel).  Completion is the host's barrier:
+ * enter it stream-ordered after mr_xchg_stream (or after cudaStreamSynchronize of it); when every rank has passed
+ * it, every slot has landed.  The normals kernel can write a rank's own rows straight into its own slot (pass
+ * the slot as out_points). */
+int mr_xchg_alloc(mr_context *ctx, size_t bytes, void **dev_ptr, unsigned char ipc_handle[64]);
+int mr_xchg_free(mr_context *ctx, void *dev_ptr);
+int mr_xchg_open(mr_context *ctx, const unsigned char ipc_handle[64], void **peer_ptr);
+int mr_xchg_close(mr_context *ctx, void *peer_ptr);
+int mr_xchg_push(mr_context *ctx, void *peer_dst, const void *src, size_t bytes);
+void *mr_xchg_stream(mr_context *ctx);
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */
 const float *mr_points_device(mr_context *ctx, int *out_count);

@@ -70,6 +70,13 @@ def load_library():
     L.mr_wait_copies_until.argtypes = [vp, C.c_int]
     L.mr_set_use_graphs.argtypes = [vp, C.c_int]
     L.mr_allgather_points.argtypes = [vp, vp, vp, C.c_int, vp, C.c_size_t, ip, ip]
+    L.mr_xchg_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    L.mr_xchg_free.argtypes = [vp, vp]
+    L.mr_xchg_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.mr_xchg_close.argtypes = [vp, vp]
+    L.mr_xchg_push.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mr_xchg_stream.argtypes = [vp]
+    L.mr_xchg_stream.restype = vp
     L.mr_graph_launch_count.argtypes = [vp]
     L.mr_graph_launch_count.restype = C.c_uint64
     L.mr_submit_main_frame.argtypes = [vp, vp, vp, C.c_int, fpp, vp, vp, vp]

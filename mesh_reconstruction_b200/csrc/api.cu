@@ -150,6 +150,10 @@ void mr_destroy(mr_context *ctx)
         if (kv.second.p) cudaFree(kv.second.p);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->h_xchg) cudaFreeHost(ctx->h_xchg);
+    for (int i = 0; i < mr_context::N_PUSH; i++) {
+        if (ctx->push_stream[i]) { cudaStreamSynchronize(ctx->push_stream[i]); cudaStreamDestroy(ctx->push_stream[i]); }
+        if (ctx->ev_push[i]) cudaEventDestroy(ctx->ev_push[i]);
+    }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int i = 0; i < 2; i++) if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
     for (int i = 0; i < 2; i++) if (ctx->ev_rows_done[i]) cudaEventDestroy(ctx->ev_rows_done[i]);

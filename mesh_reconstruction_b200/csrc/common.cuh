@@ -63,6 +63,10 @@ struct mr_context {
     int *h_count = nullptr;
     int *h_xchg = nullptr;                        // pinned per-rank counts of mr_allgather_points (exchange.cu)
     int h_xchg_cap = 0;
+    static constexpr int N_PUSH = 4;              // peer-memory pushes of mr_xchg_push go round-robin over these (exchange.cu)
+    cudaStream_t push_stream[N_PUSH] = {};
+    cudaEvent_t ev_push[N_PUSH] = {};
+    int push_next = 0;
     // pyramid geometry of compare()
     int n_levels = 0;
     int lw[MR_MAX_LEVELS], lh[MR_MAX_LEVELS];

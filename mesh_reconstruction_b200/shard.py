@@ -113,3 +113,67 @@ def allgather_points_cabi(ctx, comm, rows, count, out=None):
                                           out.shape[0], counts, C.byref(total)))
     ctx.synchronize()
     return out[:total.value], [int(c) for c in counts][:world]
+
+
+# ---- kernel-free exchange over NVLink peer memory (mr_xchg_*) --------------------------------------------------
+
+class _DevMem:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """One receive buffer per rank with a slot for every rank, mapped into every peer over CUDA IPC.
+
+    ``push()`` DMAs this rank's own slot into the same slot of every peer's buffer (copy engines over NVLink, no
+    SMs), ordered after the work queued on the context's stream; ``signal_stream()`` is the stream on which to order
+    the completion barrier (e.g. an async 4-byte all-reduce): when it has completed on every rank, every slot of
+    every buffer has landed.  Slots are ``slot_bytes`` each; ``slot(r, ...)`` views slot r of the LOCAL buffer as a
+    tensor -- pass ``slot(rank, ...)`` as the output buffer of the path so the rows are produced in place."""
+
+    def __init__(self, ctx, slot_bytes, device, group=None):
+        import ctypes as C
+        self.ctx, self.lib, self.group = ctx, ctx.lib, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        ctx.check(self.lib.mr_xchg_alloc(ctx.h, self.slot_bytes * self.world, C.byref(ptr), handle))
+        self.ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peer = {}
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            pp = C.c_void_p()
+            ctx.check(self.lib.mr_xchg_open(ctx.h, handles[p], C.byref(pp)))
+            self.peer[p] = pp.value
+
+    def slot(self, r, shape, dtype=torch.float32, offset_bytes=0):
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        return torch.as_tensor(_DevMem(self.ptr + r * self.slot_bytes + offset_bytes, shape, typestr), device=self.device)
+
+    def push(self, nbytes=None):
+        import ctypes as C
+        nbytes = self.slot_bytes if nbytes is None else int(nbytes)
+        off = self.rank * self.slot_bytes
+        for k in range(1, self.world):                       # staggered: rank r starts with peer r+1, so no peer is hit by all at once
+            p = (self.rank + k) % self.world
+            self.ctx.check(self.lib.mr_xchg_push(self.ctx.h, C.c_void_p(self.peer[p] + off), C.c_void_p(self.ptr + off), nbytes))
+
+    def signal_stream(self):
+        return torch.cuda.ExternalStream(self.lib.mr_xchg_stream(self.ctx.h), device=self.device)
+
+    def close(self):
+        import ctypes as C
+        for p, ptr in self.peer.items():
+            self.lib.mr_xchg_close(self.ctx.h, C.c_void_p(ptr))
+        self.peer = {}
+        if dist.is_initialized():
+            dist.barrier(group=self.group)                   # nobody frees a buffer a peer still has mapped
+        if self.ptr:
+            self.lib.mr_xchg_free(self.ctx.h, C.c_void_p(self.ptr))
+            self.ptr = 0

@@ -34,6 +34,27 @@ for trial, count in enumerate([1000 + 37 * rank, 0 if rank == 0 else 5, 123456 *
     ref, ref_counts = shard.allgather_points(rows, count)
     assert counts == ref_counts, (counts, ref_counts)
     assert got.shape == ref.shape and torch.equal(got, ref), trial
+# kernel-free exchange: slots pushed into the peers' buffers over NVLink (CUDA IPC), completion = tiny all-reduce
+SLOT_ROWS = 50000
+x = shard.PeerExchange(ctx, SLOT_ROWS * 28 + 4, torch.device("cuda", local))
+mine = x.slot(rank, (SLOT_ROWS, 7))
+cnt = x.slot(rank, (1,), torch.int32, offset_bytes=SLOT_ROWS * 28)
+flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+for trial in range(3):
+    src = torch.rand((SLOT_ROWS, 7), generator=g).cuda() + trial
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream)):       # producer work on the library stream
+        mine.copy_(src)
+        cnt.fill_(1000 * trial + rank)
+    x.push()
+    with torch.cuda.stream(x.signal_stream()):
+        dist.all_reduce(flag)
+    torch.cuda.synchronize()
+    ref, _ = shard.allgather_points(src, SLOT_ROWS)
+    for p in range(world):
+        assert torch.equal(x.slot(p, (SLOT_ROWS, 7)), ref[p * SLOT_ROWS:(p + 1) * SLOT_ROWS]), (trial, p)
+        assert int(x.slot(p, (1,), torch.int32, offset_bytes=SLOT_ROWS * 28)) == 1000 * trial + p
+    dist.barrier()                                                       # nobody overwrites a slot a peer is still checking
+x.close()
 # an output buffer that is too small is refused (every rank sees the same total, so every rank refuses)
 import ctypes as C
 small = torch.empty((1, 7), device="cuda")
