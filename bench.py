@@ -213,7 +213,17 @@ def main():
         # straight into its own slot, which is then DMA'd into the same slot of every peer (mr_xchg_push)
         from mesh_reconstruction_b200.shard import PeerExchange
         rows_bytes = (B * N * 28 + 255) // 256 * 256
-        xch = [PeerExchange(ctx, rows_bytes + B * 4, dev) for _ in range(nbuf)]
+        try:
+            xch = [PeerExchange(ctx, rows_bytes + B * 4, dev) for _ in range(nbuf)]
+            ok = 1
+        except Exception as e:  # noqa: BLE001  (CUDA IPC / peer access unavailable on this box)
+            print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            ok = 0
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)           # every rank must take the same path
+        if int(okt.item()) == 0:
+            use_p2p, xch = False, None
+    if use_p2p:
         rows_dev = [x.slot(rank, (B, N, 7)) for x in xch]
         counts_dev = [x.slot(rank, (B,), torch.int32, offset_bytes=rows_bytes) for x in xch]
         for c_ in counts_dev:

@@ -139,18 +139,32 @@ class PeerExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
-        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-        ctx.check(self.lib.mr_xchg_alloc(ctx.h, self.slot_bytes * self.world, C.byref(ptr), handle))
-        self.ptr = ptr.value
+        # Collective and failure-consistent: every rank reaches every collective below whatever fails locally, and
+        # either all ranks end up with a working exchange or all of them raise.
+        ptr, handle, err = C.c_void_p(), C.create_string_buffer(64), None
+        self.ptr, self.peer = 0, {}
+        if self.lib.mr_xchg_alloc(ctx.h, self.slot_bytes * self.world, C.byref(ptr), handle) == 0:
+            self.ptr = ptr.value
+        else:
+            err = self.lib.mr_last_error(ctx.h).decode()
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self.peer = {}
-        for p in range(self.world):
-            if p == self.rank:
-                continue
-            pp = C.c_void_p()
-            ctx.check(self.lib.mr_xchg_open(ctx.h, handles[p], C.byref(pp)))
-            self.peer[p] = pp.value
+        dist.all_gather_object(handles, handle.raw if self.ptr else None, group=group)
+        if err is None and any(h is None for h in handles):
+            err = "a peer could not allocate its exchange buffer"
+        if err is None:
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                pp = C.c_void_p()
+                if self.lib.mr_xchg_open(ctx.h, handles[p], C.byref(pp)) != 0:
+                    err = self.lib.mr_last_error(ctx.h).decode()
+                    break
+                self.peer[p] = pp.value
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError("peer-memory exchange unavailable: " + (err or "failed on another rank"))
 
     def slot(self, r, shape, dtype=torch.float32, offset_bytes=0):
         typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
