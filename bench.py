@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the point rows reach every rank -- p2p: copy-engine pushes into the peers' buffers over NVLink "
                          "(CUDA IPC, no SMs); nccl: all_gather_into_tensor")
+    ap.add_argument("--xchg-repeat", type=int, default=1,
+                    help="debug: push every slot this many times (emulates the per-GPU exchange volume of a larger world on few GPUs)")
     ap.add_argument("--graphs", type=int, default=None, choices=[0, 1, 2],
                     help="mr_set_use_graphs mode (default: the library's: graph replay when rows go to the host or with --farneback)")
     ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
@@ -270,7 +272,8 @@ def main():
                 # the path's one exchange step without kernels: this rank's slot (rows + counts of the step) is DMA'd
                 # into every peer's buffer over NVLink, stream-ordered after this step's kernels; a 4-byte all-reduce entered
                 # after the pushes is the completion signal (when it is done everywhere, every slot of set k has landed)
-                xch[k].push()
+                for _ in range(max(1, args.xchg_repeat)):
+                    xch[k].push()
                 with torch.cuda.stream(xch[k].signal_stream()):
                     pending[k] = (dist.all_reduce(xflag[k], async_op=True),)
             else:

@@ -8,6 +8,7 @@
 // dependency on NCCL and loads on single-GPU boxes without it.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include <vector>
@@ -191,8 +192,10 @@ extern "C" int mr_xchg_close(mr_context *ctx, void *peer_ptr)
 static int ensure_push_streams(mr_context *ctx)
 {
     if (!ctx->push_stream[0]) {
+        int lo = 0, hi = 0;
+        MR_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         for (int i = 0; i < mr_context::N_PUSH; i++) {
-            MR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->push_stream[i], cudaStreamNonBlocking));
+            MR_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->push_stream[i], cudaStreamNonBlocking, hi));   // ahead of the compute streams
             MR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_push[i], cudaEventDisableTiming));
         }
     }
@@ -220,8 +223,13 @@ extern "C" int mr_xchg_push(mr_context *ctx, void *dst, const void *src, size_t 
     MR_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_push_streams(ctx);
     if (rc) return rc;
-    const int i = ctx->push_next;
-    ctx->push_next = (i + 1) % mr_context::N_PUSH;
+    static const int n_streams = []() {                      // MR_XCHG_STREAMS=1..4 (tuning knob; default 4)
+        const char *e = getenv("MR_XCHG_STREAMS");
+        int n = e ? atoi(e) : mr_context::N_PUSH;
+        return n < 1 ? 1 : (n > mr_context::N_PUSH ? mr_context::N_PUSH : n);
+    }();
+    const int i = ctx->push_next % n_streams;
+    ctx->push_next = (i + 1) % n_streams;
     MR_CUDA(ctx, cudaEventRecord(ctx->ev_push[0], ctx->stream));
     MR_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream[i], ctx->ev_push[0], 0));
     if (bytes) MR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->push_stream[i]));
