@@ -154,12 +154,14 @@ int mr_wait_copies_until(mr_context *ctx, int max_in_flight);
  * (count x 7 floats, device memory).  out_rows (device, capacity out_capacity_rows rows -- at least the gathered
  * total on every rank) receives the rows of all ranks concatenated in RANK ORDER, which with contiguous blocks of
  * main frames per rank is the reference's append order; out_counts[world] / out_total (host, may be NULL) the
- * per-rank counts and their sum.  One 4-byte all-gather of the counts (one stream synchronisation), then one
+ * per-rank counts and their sum (64-bit: the cloud of a long clip exceeds 2^31 rows).  One small all-gather of every
+ * rank's (count, capacity) -- so that a bad argument or a too small out_rows on ANY rank makes EVERY rank return
+ * MR_EINVAL before the row exchange instead of leaving the others waiting in it (one stream synchronisation) -- then one
  * grouped NCCL operation of per-rank broadcasts with the exact counts (no padding), enqueued on mr_stream(ctx):
  * out_rows is complete after mr_synchronize().  NCCL is resolved at run time from the host process (or
  * libnccl.so.2); MR_ENODEVICE if it cannot be found. */
 int mr_allgather_points(mr_context *ctx, void *nccl_comm, const float *rows, int count, float *out_rows,
-                        size_t out_capacity_rows, int *out_counts, int *out_total);
+                        size_t out_capacity_rows, int *out_counts, long long *out_total);
 /* The same exchange WITHOUT kernels, for one process per GPU on an NVLink / NVSwitch node: every rank allocates a
  * receive buffer with one slot per rank (mr_xchg_alloc returns the device pointer and its 64-byte CUDA IPC handle),
  * the host passes the handles around (MPI, torch.distributed, a pipe ...), every rank maps its peers' buffers

@@ -69,7 +69,7 @@ def load_library():
     L.mr_wait_copies.argtypes = [vp]
     L.mr_wait_copies_until.argtypes = [vp, C.c_int]
     L.mr_set_use_graphs.argtypes = [vp, C.c_int]
-    L.mr_allgather_points.argtypes = [vp, vp, vp, C.c_int, vp, C.c_size_t, ip, ip]
+    L.mr_allgather_points.argtypes = [vp, vp, vp, C.c_int, vp, C.c_size_t, ip, C.POINTER(C.c_longlong)]
     L.mr_xchg_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
     L.mr_xchg_free.argtypes = [vp, vp]
     L.mr_xchg_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]

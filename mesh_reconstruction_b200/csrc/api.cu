@@ -8,13 +8,23 @@
 #include "jacobi3.cuh"
 
 thread_local std::string g_mr_create_error;
-int g_mr_vr_impl = 1;
-extern int g_mr_vr_tma;
+// process-wide debug knobs (mr_set_vr_impl): atomics, so that contexts driven from different threads never race on them
+std::atomic<int> g_mr_vr_impl{1};
+extern std::atomic<int> g_mr_vr_tma;
 
-size_t &mr_smem_registry(int device, const void *kernel)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel, shared by every context of this
+// process on that device: one registry per (device, kernel), only ever raised, guarded by a mutex because contexts are
+// independent and may be driven by one host thread each (SURVEY 8b "re-entrancy across different ctx").
+cudaError_t mr_ensure_smem_raw(int device, const void *kernel, size_t bytes)
 {
-    static std::map<std::pair<int, const void *>, size_t> reg;   // calls on a context are serialised by the caller
-    return reg[std::make_pair(device, kernel)];
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> reg;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = reg[std::make_pair(device, kernel)];
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 
 int mr_fail(mr_context *ctx, int code, const char *what, const char *detail)
@@ -214,8 +224,8 @@ int mr_set_use_farneback(mr_context *ctx, int on)
 // (default), 2 = fused tile kernel with plain loads
 int mr_set_vr_impl(int impl)
 {
-    g_mr_vr_impl = impl ? 1 : 0;
-    g_mr_vr_tma = impl == 2 ? 0 : 1;
+    g_mr_vr_impl.store(impl ? 1 : 0);
+    g_mr_vr_tma.store(impl == 2 ? 0 : 1);
     return MR_OK;
 }
 
@@ -236,12 +246,24 @@ int mr_load_mesh(mr_context *ctx, const float *vertices_xyzw, int n_vertices, co
     ctx->graph_warm = false;   // per-face buffers may grow: the next submission runs plainly (and allocates) again
     CHECK_ARG(ctx, n_vertices >= 0 && n_faces >= 0, "negative count");
     CHECK_ARG(ctx, n_faces == 0 || (vertices_xyzw && faces), "null mesh pointers");
-    if (n_faces == 0) return k_load_mesh(ctx, nullptr, nullptr, 0);
+    ctx->mesh_loaded = true;
+    if (n_faces == 0) return k_load_mesh(ctx, nullptr, 0, nullptr, 0, nullptr);
+    CHECK_ARG(ctx, n_vertices > 0, "faces without vertices");
     const float *dv = (const float *)mr_in(ctx, vertices_xyzw, (size_t)n_vertices * 4 * sizeof(float), "in_vtx");
     const int32_t *df = (const int32_t *)mr_in(ctx, faces, (size_t)n_faces * 3 * sizeof(int32_t), "in_faces");
-    if (!dv || !df) return mr_fail(ctx, MR_ENOMEM, "mr_load_mesh", "staging");
-    RC(k_load_mesh(ctx, dv, df, n_faces));
+    int *d_bad = mr_buf<int>(ctx, "mesh_bad", 1);
+    if (!dv || !df || !d_bad) return mr_fail(ctx, MR_ENOMEM, "mr_load_mesh", "staging");
+    MR_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    RC(k_load_mesh(ctx, dv, n_vertices, df, n_faces, d_bad));
+    MR_CUDA(ctx, cudaMemcpyAsync(ctx->h_count + 8, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_count[8]) {
+        // the offending faces were neutralised on the device (NaN corners never rasterise); unload the mesh so that a
+        // caller that ignores the error gets MR_ENOMESH instead of a silently different scene
+        ctx->F = 0;
+        ctx->mesh_loaded = false;
+        return mr_fail(ctx, MR_EINVAL, "mr_load_mesh", "a face references a vertex index outside [0, n_vertices)");
+    }
     return MR_OK;
 }
 
@@ -250,7 +272,7 @@ int mr_depth(mr_context *ctx, const float camera[16], float *out_depth)
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
     CHECK_ARG(ctx, camera && out_depth, "null argument");
-    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_depth", "loadMesh has not been called");
+    if (!ctx->mesh_loaded) return mr_fail(ctx, MR_ENOMESH, "mr_depth", "loadMesh has not been called");
     unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
     bool dev_out = mr_is_device_ptr(out_depth);
     float *d = dev_out ? out_depth : mr_buf<float>(ctx, "depth", ctx->N);
@@ -271,7 +293,7 @@ int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const
     SET_DEVICE(ctx);
     CHECK_ARG(ctx, cameras && rows && cols && out, "null argument");
     CHECK_ARG(ctx, n_cameras >= 0 && n_per_camera >= 0, "negative count");
-    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_depth_samples", "loadMesh has not been called");
+    if (!ctx->mesh_loaded) return mr_fail(ctx, MR_ENOMESH, "mr_depth_samples", "loadMesh has not been called");
     size_t total = (size_t)n_cameras * n_per_camera;
     if (total == 0) return MR_OK;
     unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
@@ -314,7 +336,7 @@ int mr_projected(mr_context *ctx, const float camera[16], const uint8_t *frame, 
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
     CHECK_ARG(ctx, camera && frame && projector && out_rgb, "null argument");
-    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_projected", "loadMesh has not been called");
+    if (!ctx->mesh_loaded) return mr_fail(ctx, MR_ENOMESH, "mr_projected", "loadMesh has not been called");
     const uint8_t *d_frame = (const uint8_t *)mr_in(ctx, frame, ctx->N, "in_side");
     unsigned long long *vis = mr_buf<unsigned long long>(ctx, "vis_main", ctx->N);
     bool dev_out = mr_is_device_ptr(out_rgb);
@@ -472,8 +494,10 @@ int mr_triangulate_pixels(mr_context *ctx, const float *const *flows, int n_side
     bool dev_out = out_points && mr_is_device_ptr(out_points);
     float *d_out = dev_out ? out_points : mr_buf<float>(ctx, "points", ctx->N * 7);
     if (!d_depth || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_triangulate_pixels", "alloc");
+    if (!dev_out && ctx->copy_pending[0]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[0], 0));
     RC(k_triangulate(ctx, d_flows, n_side, main_camera, cameras, d_depth, d_out, out_count));
     ctx->last_S = n_side;
+    ctx->last_rows = d_out;
     if (out_points && !dev_out && *out_count > 0) {
         RC(mr_out(ctx, out_points, d_out, (size_t)*out_count * 7 * sizeof(float)));
         MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -584,8 +608,8 @@ static int submit_enqueue(mr_context *ctx, const uint8_t *main_frame, const floa
                           const uint8_t *const *side_frames, const float *side_cameras, float *d_rows, int *d_cnt, bool host_rows)
 {
     // shape of the launch sequence: anything that changes the graph's topology
-    unsigned long long key = (unsigned long long)n_side | ((unsigned long long)ctx->use_farneback << 8) | ((unsigned long long)(g_mr_vr_impl & 0xff) << 9) |
-                             ((unsigned long long)(g_mr_vr_tma & 1) << 17) | ((unsigned long long)(mr_is_device_ptr(main_frame) ? 1 : 0) << 18);
+    unsigned long long key = (unsigned long long)n_side | ((unsigned long long)ctx->use_farneback << 8) | ((unsigned long long)(g_mr_vr_impl.load() & 0xff) << 9) |
+                             ((unsigned long long)(g_mr_vr_tma.load() & 1) << 17) | ((unsigned long long)(mr_is_device_ptr(main_frame) ? 1 : 0) << 18);
     // Graph replay is used when the rows go to the HOST (graphs_mode 1, the default) or always (2).  With rows left in
     // HBM there is no PCIe traffic to hide from, and with two contexts per GPU plain stream launches interleave the
     // two frames' kernels slightly better (measured at 1080p, 2 contexts: 1.24 vs 1.27 ms/pair resident, but
@@ -654,7 +678,7 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
     CHECK_ARG(ctx, main_frame && main_camera && side_frames && side_cameras && (out_count || mode == PMF_SUBMIT), "null argument");
     CHECK_ARG(ctx, n_side >= 1 && n_side <= MR_MAX_SIDE, "n_side must be in 1..MR_MAX_SIDE");
     for (int i = 0; i < n_side; i++) CHECK_ARG(ctx, side_frames[i], "null side frame");
-    if (!ctx->bufs.count("soup")) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
+    if (!ctx->mesh_loaded) return mr_fail(ctx, MR_ENOMESH, "mr_process_main_frame", "loadMesh has not been called");
     size_t N = ctx->N;
     bool dev_out = out_points && mr_is_device_ptr(out_points);
     if (mode == PMF_SUBMIT) {
@@ -666,15 +690,18 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         CHECK_ARG(ctx, !out_count || mr_is_device_ptr(out_points) == mr_is_device_ptr(out_count), "mr_submit_main_frame: out_points and out_count must live in the same memory space");
         RC(ensure_copy_stream(ctx));
         ctx->last_S = n_side;
+        ctx->last_count = -1;       // not known on the host without a synchronisation (mr_points_device reports -1)
         if (dev_out) {
             int *d_cnt = cnt_alias ? cnt_alias : mr_buf<int>(ctx, "count", 1);
             if (!d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_submit_main_frame", "alloc");
+            ctx->last_rows = out_points;
             return submit_enqueue(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, out_points, d_cnt, false);
         }
         const int slot = ctx->rows_cur;
         float *d_rows = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
         int *d_cnt = mr_buf<int>(ctx, slot ? "count1" : "count0", 1);
         if (!d_rows || !d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_submit_main_frame", "alloc");
+        ctx->last_rows = d_rows;
         // this slot's previous rows (two submissions ago) must have left for the host before they are overwritten
         if (ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
         RC(submit_enqueue(ctx, main_frame, main_camera, n_side, side_frames, side_cameras, d_rows, d_cnt, true));
@@ -704,11 +731,15 @@ static int process_main_frame_impl(mr_context *ctx, const uint8_t *main_frame, c
         slot = ctx->rows_cur;
         d_out = mr_buf<float>(ctx, slot ? "points1" : "points", N * 7);
         if (d_out && ctx->copy_pending[slot]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
-    } else
+    } else {
         d_out = mr_buf<float>(ctx, "points", N * 7);
+        // "points" doubles as row slot 0 of the pipelined calls: a copy of it may still be in flight
+        if (d_out && ctx->copy_pending[0]) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[0], 0));
+    }
     if (!d_out) return mr_fail(ctx, MR_ENOMEM, "mr_process_main_frame", "alloc");
     RC(k_triangulate(ctx, d_flows, n_side, main_camera, side_cameras, depth, d_out, out_count));   // recon.cpp:114 (syncs the stream)
     ctx->last_S = n_side;
+    ctx->last_rows = d_out;
     if (pipelined) {
         if (*out_count > 0)
             MR_CUDA(ctx, cudaMemcpyAsync(out_points, d_out, (size_t)*out_count * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -790,7 +821,7 @@ const float *mr_points_device(mr_context *ctx, int *out_count)
 {
     if (!ctx) return nullptr;
     if (out_count) *out_count = ctx->last_count;
-    return (const float *)mr_buf_raw(ctx, "points", 0);
+    return ctx->last_rows;
 }
 const float *mr_last_depth_device(mr_context *ctx) { return ctx ? (const float *)mr_buf_raw(ctx, "depth", 0) : nullptr; }
 const float *mr_last_flow_device(mr_context *ctx, int side)

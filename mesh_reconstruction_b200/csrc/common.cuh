@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,10 +57,12 @@ struct mr_context {
     std::map<std::string, DevBuf> bufs;
     // mesh (Render::loadMesh)
     int F = 0;
+    bool mesh_loaded = false;                    // a successful mr_load_mesh happened (render calls give MR_ENOMESH otherwise)
     bool use_farneback = false;   // mr_set_use_farneback: the reference's -f switch for mr_process_main_frame
     // last results
     int last_count = 0;
     int last_S = 0;
+    const float *last_rows = nullptr;            // device buffer holding the last main frame's rows (mr_points_device)
     // pinned host scratch for small readbacks
     int *h_count = nullptr;
     int *h_xchg = nullptr;                        // pinned per-rank counts of mr_allgather_points (exchange.cu)
@@ -159,20 +163,16 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel (shared by every context of
 // this process on that device): keep one registry per (device, kernel) and only ever raise the limit.
-size_t &mr_smem_registry(int device, const void *kernel);   // api.cu
+cudaError_t mr_ensure_smem_raw(int device, const void *kernel, size_t bytes);   // api.cu (mutex-guarded)
 template <class K>
 static inline cudaError_t mr_ensure_smem(mr_context *ctx, K kernel, size_t bytes)
 {
-    size_t &have = mr_smem_registry(ctx->device, (const void *)kernel);
-    if (bytes <= have) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) have = bytes;
-    return e;
+    return mr_ensure_smem_raw(ctx->device, (const void *)kernel, bytes);
 }
 
 // ---- stage launchers (all enqueue on ctx->stream; device pointers only) ------------
 // raster.cu
-int k_load_mesh(mr_context *ctx, const float *d_vtx, const int32_t *d_faces, int F);
+int k_load_mesh(mr_context *ctx, const float *d_vtx, int V, const int32_t *d_faces, int F, int *d_bad);
 int k_raster(mr_context *ctx, const Mat4 &P, unsigned long long *d_vis);
 int k_resolve_depth(mr_context *ctx, const unsigned long long *d_vis, float *d_depth);
 int k_dilate_shadow(mr_context *ctx, const float *d_depth_td, float *d_out_td);

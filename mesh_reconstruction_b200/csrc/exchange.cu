@@ -20,7 +20,7 @@ namespace {
 // stable NCCL ABI (nccl.h): opaque communicator, int result (0 = ncclSuccess), datatype enum values
 typedef void *nccl_comm_t;
 typedef int nccl_result_t;
-enum { NCCL_INT32 = 2, NCCL_FLOAT32 = 7 };
+enum { NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_FLOAT32 = 7 };
 
 struct NcclApi {
     nccl_result_t (*CommCount)(nccl_comm_t, int *) = nullptr;
@@ -34,12 +34,18 @@ struct NcclApi {
     std::string why;
 };
 
+void nccl_api_init(NcclApi &api);
+
 NcclApi &nccl_api()
 {
     static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+    static std::once_flag once;          // contexts may be driven from different host threads
+    std::call_once(once, []() { nccl_api_init(api); });
+    return api;
+}
+
+void nccl_api_init(NcclApi &api)
+{
     void *h = RTLD_DEFAULT;
     if (!dlsym(RTLD_DEFAULT, "ncclAllGather")) {
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // already mapped by the host (e.g. torch's copy)?
@@ -47,7 +53,7 @@ NcclApi &nccl_api()
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!h) {
             api.why = "NCCL not found: no ncclAllGather in the process and libnccl.so.2 cannot be loaded";
-            return api;
+            return;
         }
     }
     auto sym = [&](const char *n) { return dlsym(h, n); };
@@ -60,7 +66,6 @@ NcclApi &nccl_api()
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     api.ok = api.CommCount && api.CommUserRank && api.AllGather && api.Broadcast && api.GroupStart && api.GroupEnd;
     if (!api.ok) api.why = "NCCL library lacks a required symbol";
-    return api;
 }
 
 }  // namespace
@@ -72,53 +77,64 @@ NcclApi &nccl_api()
     } while (0)
 
 extern "C" int mr_allgather_points(mr_context *ctx, void *nccl_comm, const float *rows, int count, float *out_rows,
-                                   size_t out_capacity_rows, int *out_counts, int *out_total)
+                                   size_t out_capacity_rows, int *out_counts, long long *out_total)
 {
     if (!ctx) return MR_EINVAL;
     MR_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nccl_comm || count < 0 || (count > 0 && !rows) || !out_rows) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "bad argument");
-    if (!mr_is_device_ptr(out_rows) || (count > 0 && !mr_is_device_ptr(rows)))
-        return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "rows and out_rows must be device memory");
+    if (!nccl_comm) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "null communicator");
     NcclApi &api = nccl_api();
     if (!api.ok) return mr_fail(ctx, MR_ENODEVICE, "mr_allgather_points", api.why.c_str());
     int world = 0, rank = -1;
     MR_NCCL(ctx, api, api.CommCount(nccl_comm, &world));
     MR_NCCL(ctx, api, api.CommUserRank(nccl_comm, &rank));
     if (world < 1 || world > 4096) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "bad communicator");
-    // 1. counts: one int per rank (device all-gather, read back through the pinned scratch)
-    int *d_cnt = mr_buf<int>(ctx, "xchg_counts", (size_t)world + 1);
-    int *h_cnt = nullptr;
+    // A rank whose own arguments are bad still takes part in the first collective (with count = -1) so that EVERY rank
+    // sees the failure and none is left waiting inside the row broadcasts.
+    const bool local_bad = count < 0 || (count > 0 && !rows) || !out_rows || !mr_is_device_ptr(out_rows) || (count > 0 && !mr_is_device_ptr(rows));
+    // 1. (count, capacity) of every rank: two int64 per rank (device all-gather, read back through the pinned scratch)
+    long long *d_cnt = mr_buf<long long>(ctx, "xchg_counts", 2 * ((size_t)world + 1));
     if (!d_cnt) return mr_fail(ctx, MR_ENOMEM, "mr_allgather_points", "alloc");
-    if (ctx->h_xchg_cap < world + 1) {
+    const int need = 4 * (world + 1);                       // pinned scratch is counted in ints
+    if (ctx->h_xchg_cap < need) {
         if (ctx->h_xchg) cudaFreeHost(ctx->h_xchg);
         ctx->h_xchg = nullptr;
-        MR_CUDA(ctx, cudaMallocHost(&ctx->h_xchg, sizeof(int) * (size_t)(world + 1)));
-        ctx->h_xchg_cap = world + 1;
+        ctx->h_xchg_cap = 0;
+        MR_CUDA(ctx, cudaMallocHost(&ctx->h_xchg, sizeof(int) * (size_t)need));
+        ctx->h_xchg_cap = need;
     }
-    h_cnt = ctx->h_xchg;
-    h_cnt[world] = count;
-    MR_CUDA(ctx, cudaMemcpyAsync(d_cnt + world, h_cnt + world, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    MR_NCCL(ctx, api, api.AllGather(d_cnt + world, d_cnt, 1, NCCL_INT32, nccl_comm, ctx->stream));
-    MR_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+    long long *h_cnt = reinterpret_cast<long long *>(ctx->h_xchg);
+    h_cnt[2 * world] = local_bad ? -1 : (long long)count;
+    h_cnt[2 * world + 1] = (long long)out_capacity_rows;
+    MR_CUDA(ctx, cudaMemcpyAsync(d_cnt + 2 * world, h_cnt + 2 * world, 2 * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    MR_NCCL(ctx, api, api.AllGather(d_cnt + 2 * world, d_cnt, 2, NCCL_INT64, nccl_comm, ctx->stream));
+    MR_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 2 * sizeof(long long) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     size_t total = 0;
+    long long min_cap = -1;
+    bool any_bad = false;
     std::vector<size_t> off((size_t)world);
     for (int r = 0; r < world; r++) {
-        if (h_cnt[r] < 0) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "negative count received");
+        const long long c = h_cnt[2 * r], cap = h_cnt[2 * r + 1];
+        if (c < 0 || c > 0x7fffffffLL) any_bad = true;
         off[r] = total;
-        total += (size_t)h_cnt[r];
-        if (out_counts) out_counts[r] = h_cnt[r];
+        if (c > 0) total += (size_t)c;
+        if (min_cap < 0 || cap < min_cap) min_cap = cap;
+        if (out_counts) out_counts[r] = (int)c;
     }
-    if (out_total) *out_total = (int)total;
-    if (total > out_capacity_rows) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "out_rows is too small for the gathered rows");
+    if (out_total) *out_total = (long long)total;
+    // every rank evaluates the same two conditions on the same gathered data: the abort is collective
+    if (local_bad) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "bad argument (rows / out_rows must be device memory, count >= 0)");
+    if (any_bad) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "a rank reported a bad argument; no rows were exchanged");
+    if ((long long)total > min_cap) return mr_fail(ctx, MR_EINVAL, "mr_allgather_points", "out_rows of some rank is too small for the gathered rows; no rows were exchanged");
     // 2. rows: one broadcast per rank with its exact count, grouped into a single NCCL operation (no padding to the
     //    largest count, rows land at their final offset: rank-order concatenation == the reference's append order)
     MR_NCCL(ctx, api, api.GroupStart());
     for (int r = 0; r < world; r++) {
-        if (h_cnt[r] == 0) continue;
+        const size_t c = (size_t)h_cnt[2 * r];
+        if (c == 0) continue;
         float *dst = out_rows + off[r] * 7;
         const void *src = (r == rank) ? (const void *)rows : (const void *)dst;
-        nccl_result_t rr = api.Broadcast(src, dst, (size_t)h_cnt[r] * 7, NCCL_FLOAT32, r, nccl_comm, ctx->stream);
+        nccl_result_t rr = api.Broadcast(src, dst, c * 7, NCCL_FLOAT32, r, nccl_comm, ctx->stream);
         if (rr != 0) {
             api.GroupEnd();
             return mr_fail(ctx, MR_ECUDA, "ncclBroadcast", api.GetErrorString ? api.GetErrorString(rr) : "NCCL error");

@@ -81,7 +81,7 @@ __global__ void vr_pack_kernel(const float *__restrict__ du, const float *__rest
 }
 
 int k_vr_fused(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4);  // vr_fused.cu
-extern int g_mr_vr_impl;  // 0 = plane-per-stage, 1 = fused tiles (default)
+extern std::atomic<int> g_mr_vr_impl;  // 0 = plane-per-stage, 1 = fused tiles (default)
 
 static int vr_planes_impl(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
 {
@@ -114,7 +114,7 @@ static int vr_planes_impl(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d
 
 int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
 {
-    if (g_mr_vr_impl == 1) return k_vr_fused(ctx, d_i0, d_i1, d_flow4);
+    if (g_mr_vr_impl.load() == 1) return k_vr_fused(ctx, d_i0, d_i1, d_flow4);
     return vr_planes_impl(ctx, d_i0, d_i1, d_flow4);
 }
 

@@ -39,24 +39,34 @@ __device__ __forceinline__ float ord_to_z(unsigned int u)
 }
 
 // ---- loadMesh: de-index + dehomogenise into a triangle soup ---------------------------
-__global__ void load_mesh_kernel(const float *__restrict__ vtx, const int32_t *__restrict__ faces, int F, float *__restrict__ soup)
+// A vertex index outside [0, V) (the reference's readMesh stores -1 for an `f` line it cannot parse, util.cpp)
+// raises *bad and yields a NaN corner, which tri_setup_kernel rejects: never an out-of-bounds read.
+__global__ void load_mesh_kernel(const float *__restrict__ vtx, int V, const int32_t *__restrict__ faces, int F, float *__restrict__ soup,
+                                 int *__restrict__ bad)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F * 3) return;
-    const float *p = vtx + 4 * faces[i];
+    const int vi = faces[i];
+    if (vi < 0 || vi >= V) {
+        *bad = 1;
+        const float nan = __int_as_float(0x7fc00000);
+        soup[3 * i + 0] = soup[3 * i + 1] = soup[3 * i + 2] = nan;
+        return;
+    }
+    const float *p = vtx + 4 * (size_t)vi;
     soup[3 * i + 0] = p[0] / p[3];
     soup[3 * i + 1] = p[1] / p[3];
     soup[3 * i + 2] = p[2] / p[3];
 }
 
-int k_load_mesh(mr_context *ctx, const float *d_vtx, const int32_t *d_faces, int F)
+int k_load_mesh(mr_context *ctx, const float *d_vtx, int V, const int32_t *d_faces, int F, int *d_bad)
 {
     float *soup = mr_buf<float>(ctx, "soup", (size_t)(F > 0 ? F : 1) * 9);
     if (!soup) return mr_fail(ctx, MR_ENOMEM, "soup", "alloc");
     mr_buf<TriSetup>(ctx, "setup", (size_t)(F > 0 ? F : 1));
     ctx->F = F;
     if (F == 0) return MR_OK;
-    load_mesh_kernel<<<cdiv(F * 3, 256), 256, 0, ctx->stream>>>(d_vtx, d_faces, F, soup);
+    load_mesh_kernel<<<cdiv(F * 3, 256), 256, 0, ctx->stream>>>(d_vtx, V, d_faces, F, soup, d_bad);
     MR_LAUNCH_CHECK(ctx, "load_mesh_kernel");
     return MR_OK;
 }

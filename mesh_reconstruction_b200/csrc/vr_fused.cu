@@ -393,16 +393,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn get_encode()
 {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;          // contexts may be driven from different host threads
+    std::call_once(once, []() {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
             fn = (EncodeTiledFn)p;
         else
             cudaGetLastError();
-    }
+    });
     return fn;
 }
 
@@ -454,7 +453,7 @@ int run(mr_context *ctx, const uint8_t *g0, const uint8_t *g1, const CUtensorMap
 
 }  // namespace
 
-int g_mr_vr_tma = 1;   // 1 = stage the frames with TMA when the layout allows it, 0 = plain loads
+std::atomic<int> g_mr_vr_tma{1};   // 1 = stage the frames with TMA when the layout allows it, 0 = plain loads
 
 int k_vr_fused(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4)
 {
@@ -462,7 +461,7 @@ int k_vr_fused(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float 
     CUtensorMap tm0, tm1;
     memset(&tm0, 0, sizeof(tm0));
     memset(&tm1, 0, sizeof(tm1));
-    bool tma = g_mr_vr_tma && make_u8_map(&tm0, d_i0, ctx->W, ctx->H) && make_u8_map(&tm1, d_i1, ctx->W, ctx->H);
+    bool tma = g_mr_vr_tma.load() && make_u8_map(&tm0, d_i0, ctx->W, ctx->H) && make_u8_map(&tm1, d_i1, ctx->W, ctx->H);
     if (tma) return run<true>(ctx, d_i0, d_i1, tm0, tm1, d_flow4);
     return run<false>(ctx, d_i0, d_i1, tm0, tm1, d_flow4);
 }

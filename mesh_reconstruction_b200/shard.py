@@ -101,9 +101,15 @@ def allgather_points_cabi(ctx, comm, rows, count, out=None):
     """Variable-length all-gather of CUDA point rows through ``mr_allgather_points`` (exact counts, rank-order
     concatenation).  ctx: api.Context of this rank's GPU; comm: raw ncclComm_t.  Returns (all_rows, counts)."""
     import ctypes as C
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    counts = (C.c_int * max(world, 1))()
-    total = C.c_int(0)
+    # the communicator's own size (not torch.distributed's: the C side writes one count per NCCL rank)
+    nccl = _nccl_lib()
+    nccl.ncclCommCount.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    n = C.c_int(0)
+    if nccl.ncclCommCount(C.c_void_p(comm), C.byref(n)) != 0 or n.value < 1:
+        raise RuntimeError("ncclCommCount failed on the given communicator")
+    world = n.value
+    counts = (C.c_int * world)()
+    total = C.c_longlong(0)
     if out is None:
         cap = torch.tensor([int(count)], dtype=torch.int64, device=rows.device)
         if world > 1:

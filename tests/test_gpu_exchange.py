@@ -55,11 +55,24 @@ for trial in range(3):
         assert int(x.slot(p, (1,), torch.int32, offset_bytes=SLOT_ROWS * 28)) == 1000 * trial + p
     dist.barrier()                                                       # nobody overwrites a slot a peer is still checking
 x.close()
-# an output buffer that is too small is refused (every rank sees the same total, so every rank refuses)
+# an output buffer that is too small on ANY rank is refused on EVERY rank (the abort is collective: nobody is left
+# waiting inside the row broadcasts), and so is a bad argument on one rank only
 import ctypes as C
 small = torch.empty((1, 7), device="cuda")
-rc = ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), C.c_void_p(rows.data_ptr()), 10, C.c_void_p(small.data_ptr()), 1, None, None)
+big = torch.empty((10 * world, 7), device="cuda")
+mine_out = small if rank == world - 1 else big
+rc = ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), C.c_void_p(rows.data_ptr()), 10, C.c_void_p(mine_out.data_ptr()), mine_out.shape[0], None, None)
 assert rc == -1, rc
+host = np.zeros((4, 7), np.float32)
+src = host.ctypes.data_as(C.c_void_p) if rank == 0 else C.c_void_p(rows.data_ptr())       # rank 0 passes HOST rows
+rc = ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), src, 4, C.c_void_p(big.data_ptr()), big.shape[0], None, None)
+assert rc == -1, rc
+if rank == 0:
+    assert b"device memory" in ctx.lib.mr_last_error(ctx.h)
+tot = C.c_longlong(-1)
+rc = ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(comm), C.c_void_p(rows.data_ptr()), 10, C.c_void_p(big.data_ptr()), big.shape[0], None, C.byref(tot))
+assert rc == 0 and tot.value == 10 * world, (rc, tot.value)
+ctx.synchronize()
 dist.barrier()
 shard.destroy_raw_nccl_comm(comm)
 dist.destroy_process_group()
@@ -100,7 +113,6 @@ def test_allgather_points_argument_errors():
     import mesh_reconstruction_b200 as mr
     ctx = mr.api.Context(64, 48)
     rows = torch.zeros((4, 7), device="cuda")
-    host = np.zeros((4, 7), np.float32)
     assert ctx.lib.mr_allgather_points(ctx.h, None, C.c_void_p(rows.data_ptr()), 4, C.c_void_p(rows.data_ptr()), 4, None, None) == -1   # no communicator
-    assert ctx.lib.mr_allgather_points(ctx.h, C.c_void_p(1), host.ctypes.data_as(C.c_void_p), 4, C.c_void_p(rows.data_ptr()), 4, None, None) == -1   # host rows
-    assert b"device memory" in ctx.lib.mr_last_error(ctx.h)
+    assert b"communicator" in ctx.lib.mr_last_error(ctx.h)
+    # (host rows / too small buffers are refused collectively: covered by the worker script, which owns a communicator)
