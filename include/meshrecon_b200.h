@@ -204,6 +204,14 @@ const char *mr_stage_name(int stage);
  * csrc/jacobi3.cuh).  cov6 = c00,c01,c02,c11,c12,c22; eigenvalues descending, eigenvectors in rows. */
 int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9]);
 
+/* Diagnostics of the window-PCA normals (util.cpp:250-326) since mr_create.  The covariance of a pixel's window is
+ * evaluated from exact integer box sums for every coordinate whose values keep one sign and stay within a factor of two
+ * over the pixel's 32x24 tile (+ halo), and with the reference's own sample-by-sample double accumulation for the other
+ * coordinates; the rows are bit-identical to the reference's evaluation order either way (csrc/normals.cu).
+ * out5[0] = tiles holding valid pixels; out5[1], out5[2], out5[3] = those with one, two, three coordinates on the
+ * sample-by-sample route; out5[4] = pixels of the remaining entries that had to take that route as well. */
+int mr_normals_stats(mr_context *ctx, uint64_t out5[5]);
+
 /* Number of kernels this library launched on the context since creation (bench.py's
  * gpu_launches claim). */
 uint64_t mr_launch_count(const mr_context *ctx);

@@ -94,6 +94,7 @@ def load_library():
     L.mr_set_use_farneback.argtypes = [vp, C.c_int]
     L.mr_profile_enable.argtypes = [vp, C.c_int]
     L.mr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    L.mr_normals_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mr_stage_name.argtypes = [C.c_int]
     L.mr_stage_name.restype = C.c_char_p
     _LIB = L
@@ -158,6 +159,13 @@ class Context:
     @property
     def graph_launches(self):
         return int(self.lib.mr_graph_launch_count(self.h))
+
+    def normals_stats(self):
+        """(tiles with valid pixels, tiles with 1 / 2 / 3 coordinates on the sample-by-sample route, residual pixels) of
+        the normals covariance kernel (``mr_normals_stats``)."""
+        out = (C.c_uint64 * 5)()
+        self.check(self.lib.mr_normals_stats(self.h, out))
+        return tuple(int(v) for v in out)
 
     @property
     def launches(self):

@@ -817,6 +817,21 @@ int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9])
     return MR_OK;
 }
 
+// Counters of the window-PCA covariance kernel since the context was created (normals.cu: normals_cov_kernel)
+int mr_normals_stats(mr_context *ctx, uint64_t out5[5])
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, out5, "null argument");
+    for (int i = 0; i < 5; i++) out5[i] = 0;
+    if (!ctx->bufs.count("nrm_stats")) return MR_OK;
+    unsigned long long h[8];
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MR_CUDA(ctx, cudaMemcpy(h, mr_buf_raw(ctx, "nrm_stats", 0), sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; i++) out5[i] = h[i];
+    return MR_OK;
+}
+
 const float *mr_points_device(mr_context *ctx, int *out_count)
 {
     if (!ctx) return nullptr;

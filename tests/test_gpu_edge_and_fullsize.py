@@ -28,6 +28,9 @@ def _assert_rows(got, ref, scale, what):
     if ok.any():
         err = np.abs(got[ok, :3].astype(np.float64) / got[ok, 3:4] - ref[ok, :3].astype(np.float64) / ref[ok, 3:4]).max()
         assert err <= 1e-4 * scale, (what, err)
+    # beyond the north-star tolerance: whole rows (points AND normals) are bit-identical to the oracle's
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    assert same.all(), f"{what}: {(~same.all(1)).sum()} of {len(ref)} rows are not bit-identical (columns {np.where(~same.all(0))[0]})"
 
 
 @pytest.mark.parametrize("W,H", [(16, 12), (33, 21), (7, 5), (64, 3)])
