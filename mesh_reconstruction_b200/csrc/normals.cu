@@ -97,46 +97,58 @@ __device__ __forceinline__ void box_pass(Smem &s, const int tid, F f, long long 
     __syncthreads();
 }
 
+// One window row of the sample loop for the pixels j of a thread selected by JMASK (compile time).
+template <int NS, bool ALLVALID, int JMASK>
+__device__ __forceinline__ void sample_row(const Smem &s, const int row, const int lx, const float (*mf)[3], const double (*M)[2], double (*acc)[6])
+{
+    constexpr int NF = 3 - NS;
+#pragma unroll 7
+    for (int dx = 0; dx < WIN; dx++) {
+        const float4 v = s.tile[row][lx + dx];
+        double X[2] = {0.0, 0.0};
+        if (NF >= 1) X[0] = s.dbl[0][row][lx + dx];
+        if (NF >= 2) X[1] = s.dbl[1][row][lx + dx];
+        const bool valid = ALLVALID || v.w != 0.f;
+#pragma unroll
+        for (int j = 0; j < VR; j++) {
+            if (!(JMASK & (1 << j))) continue;
+            double D[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (k < NF) D[k] = X[k] - M[j][k];              // exact coordinate: x - mean is exact in float AND double
+                else {
+                    float f = slot(v, k) - mf[j][k];            // the reference's float-centred sample
+                    if (!ALLVALID && !valid) f = 0.f;           // invalid entries add +0 to every accumulator
+                    D[k] = (double)f;
+                }
+            }
+#pragma unroll
+            for (int b = NF; b < 3; b++)
+#pragma unroll
+                for (int a = 0; a <= b; a++) acc[j][pidx(a, b)] = __fma_rn(D[a], D[b], acc[j][pidx(a, b)]);
+        }
+    }
+}
+
 // The reference's loop for the entries that involve one of the NS inexact slots (slots 3-NS .. 2), for the three
-// vertically adjacent pixels (ly0 + j, lx) of a thread.  acc[j][pidx(a, b)] is only touched for b >= 3 - NS.
+// vertically adjacent pixels (ly0 + j, lx) of a thread: window row sy of the union serves pixel j as its row sy - j.
+// acc[j][pidx(a, b)] is only touched for b >= 3 - NS.
 template <int NS, bool ALLVALID>
 __device__ __forceinline__ void sample_loop(const Smem &s, const int ly0, const int lx, const float (*mf)[3], double (*acc)[6])
 {
     constexpr int NF = 3 - NS;
+    static_assert(VR == 3, "row schedule below is written for three pixels per thread");
     double M[VR][2];
 #pragma unroll
     for (int j = 0; j < VR; j++)
 #pragma unroll
         for (int k = 0; k < 2; k++) M[j][k] = k < NF ? (double)mf[j][k] : 0.0;
+    sample_row<NS, ALLVALID, 1>(s, ly0 + 0, lx, mf, M, acc);
+    sample_row<NS, ALLVALID, 3>(s, ly0 + 1, lx, mf, M, acc);
 #pragma unroll 1
-    for (int sy = 0; sy < WIN + VR - 1; sy++) {
-#pragma unroll 3
-        for (int dx = 0; dx < WIN; dx++) {
-            const float4 v = s.tile[ly0 + sy][lx + dx];
-            double X[2] = {0.0, 0.0};
-            if (NF >= 1) X[0] = s.dbl[0][ly0 + sy][lx + dx];
-            if (NF >= 2) X[1] = s.dbl[1][ly0 + sy][lx + dx];
-            const bool valid = ALLVALID || v.w != 0.f;
-#pragma unroll
-            for (int j = 0; j < VR; j++) {
-                if (sy - j < 0 || sy - j >= WIN) continue;          // uniform per sy
-                double D[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (k < NF) D[k] = X[k] - M[j][k];              // exact coordinate: x - mean is exact in float AND double
-                    else {
-                        float f = slot(v, k) - mf[j][k];            // the reference's float-centred sample
-                        if (!valid) f = 0.f;                        // invalid entries add +0 to every accumulator
-                        D[k] = (double)f;
-                    }
-                }
-#pragma unroll
-                for (int b = NF; b < 3; b++)
-#pragma unroll
-                    for (int a = 0; a <= b; a++) acc[j][pidx(a, b)] = __fma_rn(D[a], D[b], acc[j][pidx(a, b)]);
-            }
-        }
-    }
+    for (int sy = 2; sy < WIN; sy++) sample_row<NS, ALLVALID, 7>(s, ly0 + sy, lx, mf, M, acc);
+    sample_row<NS, ALLVALID, 6>(s, ly0 + WIN, lx, mf, M, acc);
+    sample_row<NS, ALLVALID, 4>(s, ly0 + WIN + 1, lx, mf, M, acc);
 }
 
 // plain six-accumulator loop for ONE pixel (window origin ly, lx), the mean being known; slots < n_int hold integers
@@ -432,12 +444,17 @@ __global__ void __launch_bounds__(NT, 2) normals_cov_kernel(const float4 *__rest
             const long long n0 = (valid && f0) ? __float2int_rn((v.x - c0) * sc0) : 0;
             m[0] = valid ? 1 : 0; m[1] = n0; m[2] = n0 * n0; }, A);
     }
-    // ---- mean: float sums in window scan order (row-major inside the window), MRUN adjacent pixels per thread -------------
+    // ---- mean: float sums in window scan order (row-major inside the window), MRUN adjacent pixels per thread.  Packed
+    // f32x2 adds (two IEEE round-to-nearest additions per instruction): (x, y) of one pixel, z of two adjacent pixels;
+    // where only one of the pair uses the sample the other adds 0, which changes nothing ------------------------------
     if (tid < TY * (TX / MRUN)) {
+        static_assert(MRUN == 4, "z chains are packed in pixel pairs");
         const int r = tid % TY, c0 = (tid / TY) * MRUN;
-        float sx[MRUN], sy[MRUN], sz[MRUN];
+        float2 sxy[MRUN], sz[MRUN / 2];
 #pragma unroll
-        for (int j = 0; j < MRUN; j++) sx[j] = sy[j] = sz[j] = 0.f;
+        for (int j = 0; j < MRUN; j++) sxy[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < MRUN / 2; j++) sz[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int dy = 0; dy < WIN; dy++) {
             const float4 *trow = &s.tile[r + dy][c0];
@@ -446,11 +463,16 @@ __global__ void __launch_bounds__(NT, 2) normals_cov_kernel(const float4 *__rest
                 const float4 v = trow[dx];           // invalid entries are all-zero: x + 0 == x
 #pragma unroll
                 for (int j = 0; j < MRUN; j++)
-                    if (dx - j >= 0 && dx - j < WIN) { sx[j] = sx[j] + v.x; sy[j] = sy[j] + v.y; sz[j] = sz[j] + v.z; }
+                    if (dx - j >= 0 && dx - j < WIN) sxy[j] = __fadd2_rn(sxy[j], make_float2(v.x, v.y));
+#pragma unroll
+                for (int j = 0; j < MRUN; j += 2) {
+                    const bool u0 = dx - j >= 0 && dx - j < WIN, u1 = dx - j - 1 >= 0 && dx - j - 1 < WIN;
+                    if (u0 || u1) sz[j / 2] = __fadd2_rn(sz[j / 2], make_float2(u0 ? v.z : 0.f, u1 ? v.z : 0.f));
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < MRUN; j++) s.mean[r][c0 + j] = make_float4(sx[j], sy[j], sz[j], 0.f);
+        for (int j = 0; j < MRUN; j++) s.mean[r][c0 + j] = make_float4(sxy[j].x, sxy[j].y, (j & 1) ? sz[j / 2].y : sz[j / 2].x, 0.f);
     }
     __syncthreads();
     switch (ti.ns) {

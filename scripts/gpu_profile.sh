@@ -5,7 +5,7 @@
 #   bench_$1.json    -- a clean (un-profiled) bench line
 TAG=${1:-run}
 KREGEX=${2:-normals_kernel}
-OURS='regex:^(vr_|raster_|tri_setup|resolve_depth|dilate_|row_prefix|shade_|mix_back|remap_|pyr_|absdiff|strided_copy|sobel_|triangulate_|deh_|normals_|moments_|count_|load_mesh|zero_channel|DeviceScan)'
+OURS='regex:^(vr_|raster_|tri_setup|resolve_depth|dilate_|row_prefix|shade_|mix_back|remap_|pyr_|absdiff|strided_copy|sobel_|triangulate_|deh_|normals_|moments_|normals_|count_|load_mesh|zero_channel|DeviceScan)'
 mkdir -p gpurun_out
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -c 3000 gpurun_out/bench_$TAG.json
