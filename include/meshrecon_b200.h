@@ -178,6 +178,33 @@ int mr_xchg_open(mr_context *ctx, const unsigned char ipc_handle[64], void **pee
 int mr_xchg_close(mr_context *ctx, void *peer_ptr);
 int mr_xchg_push(mr_context *ctx, void *peer_dst, const void *src, size_t bytes);
 void *mr_xchg_stream(mr_context *ctx);
+/* ---- Heuristic::filterPoints  heuristic.cpp:55-176 ------------------------------------------------
+ * The step that consumes the gathered cloud after every pass over the main frames (recon.cpp:125): outlier / redundancy
+ * filter by local density -- radius-neighbour table restricted to j < i, clamped power iteration (up to 200 sweeps),
+ * greedy thinning along descending density, compaction in ascending index order.  Running it on the device means that
+ * only the SURVIVING rows have to cross PCIe for the CPU meshing step.
+ *   points_xyzw: n x 4 homogeneous (dehomogenised like util.cpp:16-29), normals_xyz: n x 3 or NULL, host or device.
+ *   radius: alphaVals.back() / 4 (heuristic.cpp:63).  NOTE the reference compares it with FLANN L2_Simple distances,
+ *   which are SQUARED Euclidean distances; so does this function.
+ *   out_points_xyzw / out_normals_xyz (capacity n rows) / out_keep (capacity n, the surviving indices, ascending): host
+ *   or device, each may be NULL; *out_count = number of survivors.
+ * Bit-identical to the CPU restatement (oracle/filter_oracle.cpp) including the double accumulations over all pairs.
+ * Two things the reference leaves to its libraries are defined: the neighbour set is the
+ * exact radius set (the reference's FLANN kd-tree search is randomised and approximate), and points of EQUAL density
+ * are visited in descending index order (cv::sortIdx leaves their order to std::sort).
+ * mr_filter_rows is the same for n x 7 point rows (x, y, z, w, nx, ny, nz) as produced by the path. */
+int mr_filter_points(mr_context *ctx, const float *points_xyzw, const float *normals_xyz, size_t n, float radius,
+                     float *out_points_xyzw, float *out_normals_xyz, int32_t *out_keep, size_t *out_count);
+int mr_filter_rows(mr_context *ctx, const float *rows7, size_t n, float radius, float *out_rows7, int32_t *out_keep,
+                   size_t *out_count);
+/* Facts about the last mr_filter_points / mr_filter_rows of the context: info3 = neighbour pairs (j < i), power
+ * iterations run, thinning rounds; density / score (n floats each, host or device, may be NULL) = the converged density
+ * and the raw score of the last iteration (heuristic.cpp:104-138), for tests. */
+int mr_filter_info(mr_context *ctx, long long info3[3], float *density, float *score);
+/* Test hook: left-to-right double accumulation of n non-negative float terms, evaluated in parallel but bit-identical to
+ * the sequential loop (the primitive behind the reference's `sum +=` / `change +=`, heuristic.cpp:117,133). */
+int mr_debug_seqsum(mr_context *ctx, const float *terms, size_t n, double *out);
+
 /* Device pointer to the point rows produced by the last mr_process_main_frame /
  * mr_triangulate_pixels (valid until the next call), and their count. */
 const float *mr_points_device(mr_context *ctx, int *out_count);

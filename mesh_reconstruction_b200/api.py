@@ -95,6 +95,10 @@ def load_library():
     L.mr_profile_enable.argtypes = [vp, C.c_int]
     L.mr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.mr_normals_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mr_filter_points.argtypes = [vp, vp, vp, C.c_size_t, C.c_float, vp, vp, vp, C.POINTER(C.c_size_t)]
+    L.mr_filter_rows.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, vp, C.POINTER(C.c_size_t)]
+    L.mr_filter_info.argtypes = [vp, C.POINTER(C.c_longlong), vp, vp]
+    L.mr_debug_seqsum.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_double)]
     L.mr_stage_name.argtypes = [C.c_int]
     L.mr_stage_name.restype = C.c_char_p
     _LIB = L
@@ -382,3 +386,60 @@ def submit_main_frame(render, main_frame, main_camera, side_frames, side_cameras
     po, ko = _ptr(out, np.float32)
     pc = _ptr(out_count, np.int32)[0] if out_count is not None else None
     ctx.check(ctx.lib.mr_submit_main_frame(ctx.h, pf, pm, S, arr, cams.ctypes.data, po, pc))
+
+
+def filterPoints(points, normals, radius, device=0, ctx=None, want_info=False):
+    """``Heuristic::filterPoints(Mat &points, Mat &normals)`` (heuristic.cpp:55-176) on the GPU.  ``points`` n x 4
+    homogeneous, ``normals`` n x 3 (or None), NumPy or CUDA tensors; ``radius`` is ``alphaVals.back() / 4`` and, as in
+    the reference, bounds SQUARED distances.  Returns (points, normals, keep) of the survivors in ascending index order
+    -- NumPy for NumPy inputs, CUDA tensors (views of fresh buffers) for CUDA inputs -- plus an info dict if asked."""
+    ctx = ctx or _ctx(16, 16, device)
+    n = int(points.shape[0])
+    cnt = C.c_size_t(0)
+    pp, kp = _ptr(points, np.float32)
+    pn, kn = (_ptr(normals, np.float32) if normals is not None else (None, None))
+    if _is_torch(points):
+        import torch
+        op = torch.empty((max(n, 1), 4), dtype=torch.float32, device=points.device)
+        on = torch.empty((max(n, 1), 3), dtype=torch.float32, device=points.device) if normals is not None else None
+        ok = torch.empty(max(n, 1), dtype=torch.int32, device=points.device)
+        ptrs = (op.data_ptr(), on.data_ptr() if on is not None else None, ok.data_ptr())
+    else:
+        op = np.empty((max(n, 1), 4), np.float32)
+        on = np.empty((max(n, 1), 3), np.float32) if normals is not None else None
+        ok = np.empty(max(n, 1), np.int32)
+        ptrs = (op.ctypes.data, on.ctypes.data if on is not None else None, ok.ctypes.data)
+    ctx.check(ctx.lib.mr_filter_points(ctx.h, pp, pn, n, float(radius), ptrs[0], ptrs[1], ptrs[2], C.byref(cnt)))
+    m = cnt.value
+    res = (op[:m], on[:m] if on is not None else None, ok[:m])
+    return res + (filter_info(ctx),) if want_info else res
+
+
+def filter_rows(rows7, radius, device=0, ctx=None, out=None):
+    """``mr_filter_rows``: the same filter on n x 7 point rows (x, y, z, w, nx, ny, nz).  Returns (rows, keep)."""
+    ctx = ctx or _ctx(16, 16, device)
+    n = int(rows7.shape[0])
+    cnt = C.c_size_t(0)
+    pr, kr = _ptr(rows7, np.float32)
+    if _is_torch(rows7):
+        import torch
+        orows = out if out is not None else torch.empty((max(n, 1), 7), dtype=torch.float32, device=rows7.device)
+        ok = torch.empty(max(n, 1), dtype=torch.int32, device=rows7.device)
+        po, pk = orows.data_ptr(), ok.data_ptr()
+    else:
+        orows = out if out is not None else np.empty((max(n, 1), 7), np.float32)
+        ok = np.empty(max(n, 1), np.int32)
+        po, pk = (orows.data_ptr() if _is_torch(orows) else orows.ctypes.data), ok.ctypes.data
+    ctx.check(ctx.lib.mr_filter_rows(ctx.h, pr, n, float(radius), po, pk, C.byref(cnt)))
+    return orows[:cnt.value], ok[:cnt.value]
+
+
+def filter_info(ctx, want_arrays=False, n=None):
+    """Facts about the context's last filter call: edges (j < i neighbour pairs), power iterations, thinning rounds."""
+    info = (C.c_longlong * 3)()
+    if want_arrays:
+        density, score = np.empty(n, np.float32), np.empty(n, np.float32)
+        ctx.check(ctx.lib.mr_filter_info(ctx.h, info, density.ctypes.data, score.ctypes.data))
+        return {"n_edges": info[0], "iters": info[1], "rounds": info[2], "density": density, "score": score}
+    ctx.check(ctx.lib.mr_filter_info(ctx.h, info, None, None))
+    return {"n_edges": info[0], "iters": info[1], "rounds": info[2]}

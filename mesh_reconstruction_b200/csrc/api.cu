@@ -817,6 +817,82 @@ int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9])
     return MR_OK;
 }
 
+// Heuristic::filterPoints (heuristic.cpp:55-176) on the device.  points: n x 4 (stride ps floats), normals: n x 3 (stride ns) or
+// null; host or device memory (host inputs are staged).  Outputs likewise; out_points / out_normals / out_keep may be null.
+static int filter_impl(mr_context *ctx, const float *points, int ps, const float *normals, int ns, size_t n, float radius, float *out_points,
+                       int ops, float *out_normals, int ons, int32_t *out_keep, size_t *out_count, bool rows7)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, out_count, "null out_count");
+    *out_count = 0;
+    CHECK_ARG(ctx, n <= 0x7fffffffu, "too many points");
+    CHECK_ARG(ctx, n == 0 || points, "null points");
+    CHECK_ARG(ctx, radius == radius, "radius is NaN");
+    ctx->filter_info[0] = ctx->filter_info[1] = ctx->filter_info[2] = 0;
+    ctx->filter_n = (int)n;
+    if (n == 0) return MR_OK;
+    const bool in_dev = mr_is_device_ptr(points);
+    CHECK_ARG(ctx, !normals || rows7 || mr_is_device_ptr(normals) == in_dev, "points and normals must live in the same memory space");
+    const float *d_pts = (const float *)mr_in(ctx, points, n * (size_t)ps * sizeof(float), "fl_in_pts");
+    const float *d_nrm = nullptr;
+    if (rows7) d_nrm = d_pts + 4;
+    else if (normals) d_nrm = (const float *)mr_in(ctx, normals, n * (size_t)ns * sizeof(float), "fl_in_nrm");
+    if (!d_pts || (normals && !d_nrm)) return mr_fail(ctx, MR_ENOMEM, "mr_filter_points", "staging");
+    const bool out_dev_p = out_points && mr_is_device_ptr(out_points), out_dev_k = out_keep && mr_is_device_ptr(out_keep);
+    const bool out_dev_n = out_normals && mr_is_device_ptr(out_normals);
+    CHECK_ARG(ctx, !(out_dev_p && out_points == points), "in-place filtering of device buffers is not supported");
+    float *d_op = out_points ? (out_dev_p ? out_points : mr_buf<float>(ctx, "fl_out_pts", n * (size_t)ops)) : nullptr;
+    float *d_on = nullptr;
+    if (rows7) d_on = d_op ? d_op + 4 : nullptr;
+    else if (out_normals) d_on = out_dev_n ? out_normals : mr_buf<float>(ctx, "fl_out_nrm", n * (size_t)ons);
+    int *d_ok = out_keep ? (out_dev_k ? out_keep : mr_buf<int>(ctx, "fl_out_keep", n)) : nullptr;
+    if ((out_points && !d_op) || (out_normals && !rows7 && !d_on) || (out_keep && !d_ok)) return mr_fail(ctx, MR_ENOMEM, "mr_filter_points", "alloc");
+    int m = 0;
+    RC(k_filter_points(ctx, d_pts, ps, d_nrm, ns, (int)n, radius, d_op, ops, d_on, ons, d_ok, &m, ctx->filter_info));
+    *out_count = (size_t)m;
+    if (m > 0) {
+        if (out_points && !out_dev_p) RC(mr_out(ctx, out_points, d_op, (size_t)m * ops * sizeof(float)));
+        if (out_normals && !rows7 && !out_dev_n) RC(mr_out(ctx, out_normals, d_on, (size_t)m * ons * sizeof(float)));
+        if (out_keep && !out_dev_k) RC(mr_out(ctx, out_keep, d_ok, (size_t)m * sizeof(int)));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_filter_points(mr_context *ctx, const float *points_xyzw, const float *normals_xyz, size_t n, float radius, float *out_points_xyzw,
+                     float *out_normals_xyz, int32_t *out_keep, size_t *out_count)
+{
+    return filter_impl(ctx, points_xyzw, 4, normals_xyz, 3, n, radius, out_points_xyzw, 4, out_normals_xyz, 3, out_keep, out_count, false);
+}
+
+int mr_filter_rows(mr_context *ctx, const float *rows7, size_t n, float radius, float *out_rows7, int32_t *out_keep, size_t *out_count)
+{
+    return filter_impl(ctx, rows7, 7, rows7 ? rows7 + 4 : nullptr, 7, n, radius, out_rows7, 7, nullptr, 7, out_keep, out_count, true);
+}
+
+int mr_filter_info(mr_context *ctx, long long info3[3], float *density, float *score)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    if (info3) for (int i = 0; i < 3; i++) info3[i] = ctx->filter_info[i];
+    const size_t n = (size_t)ctx->filter_n;
+    if (n && density) MR_CUDA(ctx, cudaMemcpy(density, mr_buf_raw(ctx, "fl_density", 0), n * sizeof(float), cudaMemcpyDefault));
+    if (n && score) MR_CUDA(ctx, cudaMemcpy(score, mr_buf_raw(ctx, "fl_score", 0), n * sizeof(float), cudaMemcpyDefault));
+    return MR_OK;
+}
+
+// test hook: the exact emulation of a left-to-right double accumulation of non-negative float terms (filter.cu: seqsum)
+int mr_debug_seqsum(mr_context *ctx, const float *terms, size_t n, double *out)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, out && (terms || n == 0), "null argument");
+    const float *d = n ? (const float *)mr_in(ctx, terms, n * sizeof(float), "fl_dbg_terms") : nullptr;
+    if (n && !d) return mr_fail(ctx, MR_ENOMEM, "mr_debug_seqsum", "staging");
+    return k_seqsum(ctx, d, (long long)n, out);
+}
+
 // Counters of the window-PCA covariance kernel since the context was created (normals.cu: normals_cov_kernel)
 int mr_normals_stats(mr_context *ctx, uint64_t out5[5])
 {

@@ -63,6 +63,8 @@ struct mr_context {
     int last_count = 0;
     int last_S = 0;
     const float *last_rows = nullptr;            // device buffer holding the last main frame's rows (mr_points_device)
+    long long filter_info[3] = {0, 0, 0};        // last mr_filter_points: neighbour pairs, power iterations, thinning rounds
+    int filter_n = 0;
     // pinned host scratch for small readbacks
     int *h_count = nullptr;
     int *h_xchg = nullptr;                        // pinned per-rank counts of mr_allgather_points (exchange.cu)
@@ -187,6 +189,10 @@ int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const 
 int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off);
 int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4);   // farneback.cu
 int mr_flow_init_tables(mr_context *ctx);
+// filter.cu
+int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const float *d_nrm, int nstride, int n, float radius, float *d_out_pts,
+                    int opstride, float *d_out_nrm, int onstride, int *d_out_keep, int *h_count, long long *info);
+int k_seqsum(mr_context *ctx, const float *d_terms, long long n, double *h_out);
 // tri.cu
 int k_image_gradient(mr_context *ctx, const float *d_img, float *d_grad2);
 int k_triangulate(mr_context *ctx, const float *const *d_flows_host_array, int S, const float *Pmain, const float *cams,
