@@ -5,9 +5,10 @@
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU arithmetic (oracle)
 
 Metric: Mpix/s matched + triangulated = pixels of all processed (main, side) pairs / time.
-Workload (config 4 of BASELINE.json): synthetic 1920x1080 300-frame sequence, adjacent-pair
-matching (main i, side i+1, S = 1).  One "step" = `--pairs` frame pairs per GPU through the whole
-path (depth raster -> shadow raster + dilation -> reproject + mixBackground -> variational
+Workload (config 4 of BASELINE.json, the headline): synthetic 1920x1080 300-frame sequence,
+adjacent-pair matching (main i, side i+1, S = 1); `--config 5`: synthetic 3840x2160 600-frame
+sequence, multi-baseline (S = 4, sides i-2, i-1, i+1, i+2).  One "step" = `--pairs` main frames
+per GPU (S pairs each) through the whole path (depth raster -> shadow raster + dilation -> reproject + mixBackground -> variational
 refinement -> cubic remap -> pyramid compare -> Newton triangulation -> PCA normals), plus, for
 N > 1, the NCCL all-gather of the point rows.  Frame pairs shard across ranks (weak scaling).
 
@@ -80,8 +81,47 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in bits.items() if self.reasons & b], "samples": len(sm)}
 
 
+def sides_of(a, S):
+    """side frames of main frame a: a+1 (S = 1, config 4), a-1 / a+1 (S = 2), a-2, a-1, a+1, a+2 (S = 4, config 5)"""
+    return [a + 1] if S == 1 else ([a - 1, a + 1] if S == 2 else [a - 2, a - 1, a + 1, a + 2])
+
+
+def main_range(n_local, S):
+    """main frames of a block of n_local frames whose side frames all lie inside the block"""
+    h = S // 2
+    return (h, n_local - h) if S > 1 else (0, n_local - 1)
+
+
+def bind_to_gpu_numa(local, diag):
+    """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated: first-touch then places
+    the row / frame buffers in the memory next to the GPU's PCIe root, so that the D2H row traffic of the ranks does not
+    cross the socket interconnect (e2e flattens at ~89 GB/s aggregate from 2 GPUs on)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(local)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                      # sysfs uses a 4-digit PCI domain
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = []
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        diag["numa_node"] = node
+        if node >= 0 and allowed:
+            os.sched_setaffinity(0, allowed)
+            diag["numa_bound_cpus"] = len(allowed)
+    except Exception as e:  # noqa: BLE001
+        diag["numa_bind_error"] = str(e)[:120]
+
+
 def cpu_reference_pairs(scene, frames, pairs, threads, farneback=False):
-    """Times the CPU oracle (reference arithmetic) on the given (main, side) index pairs."""
+    """Times the CPU oracle (reference arithmetic) on the given (main, [sides]) jobs (a bare side index = one side)."""
     import cv2
     from oracle.pipeline import process_main_frame
     from oracle.render import RenderOracle
@@ -92,9 +132,16 @@ def cpu_reference_pairs(scene, frames, pairs, threads, farneback=False):
     t0 = time.perf_counter()
     pts = 0
     for fa, fb in pairs:
-        tri = process_main_frame(r, frames, scene.cameras, fa, [fb], use_farneback=farneback)
+        tri = process_main_frame(r, frames, scene.cameras, fa, list(fb) if isinstance(fb, (list, tuple)) else [fb], use_farneback=farneback)
         pts += len(tri)
     return time.perf_counter() - t0, pts
+
+
+def workload_name(args):
+    W, H, S = args.width, args.height, args.sides
+    if args.config == 5:
+        return f"synthetic {W}x{H} {args.frames}-frame sequence, multi-baseline matching (S={S}: sides i-2, i-1, i+1, i+2) + triangulation (BASELINE config 5)"
+    return f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S={S} (BASELINE config 4)"
 
 
 def run_reference(args):
@@ -107,25 +154,28 @@ def run_reference(args):
     from mesh_reconstruction_b200 import synth
     W, H = args.width, args.height
     cores = os.cpu_count() or 1
-    scene = synth.make_scene(W, H, 4, step=args.cam_step, mesh_err=args.mesh_err)
-    frames = {i: scene.frame(i) for i in range(4)}
-    pairs_cycle = [(0, 1), (1, 2), (2, 3)]
-    if args.warmup > 0:      # one real warm-up pair is enough (each pair is seconds of CPU work)
+    S = args.sides
+    nfr = 4 + 2 * (S // 2) if S > 1 else 4
+    scene = synth.make_scene(W, H, nfr, step=args.cam_step, mesh_err=args.mesh_err)
+    frames = {i: scene.frame(i) for i in range(nfr)}
+    lo, hi = main_range(nfr, S)
+    pairs_cycle = [(a, sides_of(a, S)) for a in range(lo, hi)]
+    if args.warmup > 0:      # one real warm-up main frame is enough (each is seconds of CPU work)
         cpu_reference_pairs(scene, frames, [pairs_cycle[0]], cores, args.farneback)
     t_total = 0.0
     for k in range(args.steps):
-        t, _ = cpu_reference_pairs(scene, frames, [pairs_cycle[k % 3]], cores, args.farneback)
+        t, _ = cpu_reference_pairs(scene, frames, [pairs_cycle[k % len(pairs_cycle)]], cores, args.farneback)
         t_total += t
-    pix = args.steps * W * H
+    pix = args.steps * W * H * S
     val = pix / t_total / 1e6
     line = {
         "impl": "reference", "metric": "Mpix/s matched+triangulated", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {W}x{H} sequence, adjacent-pair matching + triangulation, S=1",
-                   "pairs_per_step": 1, "sample": "1 frame pair per step (bounded sample of the 299-pair workload)"},
+        "config": {"workload": workload_name(args), "main_frames_per_step": 1, "side_frames": S,
+                   "sample": f"1 main frame ({S} frame pair{'s' if S > 1 else ''}) per step (bounded sample of the {args.frames}-frame workload)"},
         "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} frame pairs of {W}x{H}, cv2 {__import__('cv2').__version__} with {cores} threads + C restatement (OpenMP)"},
+                         "sample": f"{args.steps} main frames x {S} side frames of {W}x{H}, cv2 {__import__('cv2').__version__} with {cores} threads + C restatement (OpenMP)"},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -138,10 +188,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--pairs", type=int, default=8, help="frame pairs per GPU per step")
-    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--config", type=int, default=4, choices=[4, 5],
+                    help="BASELINE.json config: 4 = synthetic 1920x1080 x300, adjacent pairs (S = 1, the headline); "
+                         "5 = synthetic 3840x2160 x600, multi-baseline (S = 4, side frames i-2, i-1, i+1, i+2)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--sides", type=int, default=None, choices=[1, 2, 4], help="side cameras per main frame (default: 1 for config 4, 4 for config 5)")
+    ap.add_argument("--pairs", type=int, default=None, help="MAIN frames per GPU per step (each with S side frames); default 8 (config 4) / 4 (config 5)")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this rank (and its pinned host buffers) to the CPUs local to its GPU")
+    ap.add_argument("--link-probe-s", type=float, default=0.3, help="seconds of the all-ranks D2H probe that measures the host link ceiling (0 = skip)")
     ap.add_argument("--cam-step", type=float, default=0.006)
     ap.add_argument("--mesh-err", type=float, default=0.02)
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame pairs timed for cpu_baseline (rank 0, N=1)")
@@ -157,6 +213,12 @@ def main():
                     help="mr_set_use_graphs mode (default: the library's: graph replay when rows go to the host or with --farneback)")
     ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
     args = ap.parse_args()
+    cfg5 = args.config == 5
+    args.width = args.width or (3840 if cfg5 else 1920)
+    args.height = args.height or (2160 if cfg5 else 1080)
+    args.frames = args.frames or (600 if cfg5 else 300)
+    args.sides = args.sides or (4 if cfg5 else 1)
+    args.pairs = args.pairs or (4 if cfg5 else 8)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -170,11 +232,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    diag0 = {}
+    affinity0 = os.sched_getaffinity(0)
+    if not args.no_numa_bind:
+        bind_to_gpu_numa(local, diag0)          # before the first pinned allocation
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    W, H, B, K, Wm = args.width, args.height, args.pairs, args.steps, args.warmup
+    W, H, B, K, Wm, S = args.width, args.height, args.pairs, args.steps, args.warmup, args.sides
     N = W * H
     lib = mr.load_library()
     if args.vr_impl is not None:
@@ -184,7 +250,7 @@ def main():
     scene = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err)
     block = max(2, args.frames // world)
     start = rank * block
-    n_local = min(block, B * (K + Wm) + 1, args.frames - start)
+    n_local = min(block, B * (K + Wm) + 1 + 2 * (S // 2), args.frames - start)
     idx = [start + i for i in range(n_local)]
     frames_dev = [scene.frame_torch(i, dev).contiguous() for i in idx]
     frames_pin = [f.cpu().pin_memory() for f in frames_dev]
@@ -215,11 +281,15 @@ def main():
         # straight into its own slot, which is then DMA'd into the same slot of every peer (mr_xchg_push)
         from mesh_reconstruction_b200.shard import PeerExchange
         rows_bytes = (B * N * 28 + 255) // 256 * 256
+        xch = []
         try:
-            xch = [PeerExchange(ctx, rows_bytes + B * 4, dev) for _ in range(nbuf)]
+            for _ in range(nbuf):
+                xch.append(PeerExchange(ctx, rows_bytes + B * 4, dev))      # collective; raises on every rank or on none
             ok = 1
         except Exception as e:  # noqa: BLE001  (CUDA IPC / peer access unavailable on this box)
             print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            for x in xch:                    # an exchange that was already built must not stay mapped in the peers
+                x.close()
             ok = 0
         okt = torch.tensor([ok], dtype=torch.int32, device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)           # every rank must take the same path
@@ -244,9 +314,11 @@ def main():
     gather_counts = [torch.empty((world * B,), dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 and not use_p2p else None
     pending = [None] * nbuf
 
-    def pair(j):                      # j-th pair of this rank, cycling inside its block
-        a = j % (n_local - 1)
-        return a, a + 1
+    m_lo, m_hi = main_range(n_local, S)
+
+    def pair(j):                      # j-th main frame of this rank (cycling inside its block) and its side frames
+        a = m_lo + j % (m_hi - m_lo)
+        return a, sides_of(a, S)
 
     def wait_pending(k):
         # make the LIBRARY stream (not torch's current stream) wait for the collective that still reads buffer k
@@ -263,8 +335,8 @@ def main():
         k = s % nbuf
         wait_pending(k)
         for b in range(B):
-            a, c = pair(s * B + b)
-            mr.submit_main_frame(renders[b % nctx], frames_dev[a], cams[idx[a]], [frames_dev[c]], [cams[idx[c]]],
+            a, cs = pair(s * B + b)
+            mr.submit_main_frame(renders[b % nctx], frames_dev[a], cams[idx[a]], [frames_dev[c] for c in cs], [cams[idx[c]] for c in cs],
                                  out=rows_dev[k][b], out_count=counts_dev[k][b:b + 1])
         if world > 1:
             join_streams()
@@ -291,8 +363,8 @@ def main():
         # pipeline of pinned buffer sets, the way a long-running reconstruction consumes its main frames.
         k = s & 1
         for b in range(B):
-            a, c = pair(s * B + b)
-            mr.submit_main_frame(renders[b % nctx], frames_pin[a], cams[idx[a]], [frames_pin[c]], [cams[idx[c]]],
+            a, cs = pair(s * B + b)
+            mr.submit_main_frame(renders[b % nctx], frames_pin[a], cams[idx[a]], [frames_pin[c] for c in cs], [cams[idx[c]] for c in cs],
                                  out=rows_pin[k][b], out_count=counts_pin[k][b:b + 1])
         for c_, r_ in enumerate(renders):
             r_.ctx.wait_copies_until(per_ctx[c_])
@@ -308,7 +380,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    diag = {}
+    diag = dict(diag0)
 
     def timed(fn, steps, first, drain=None):
         for k in range(nbuf):
@@ -380,74 +452,170 @@ def main():
         diag_res["clock_reason_bits_by_rank"] = [int(v) for v in allh[:, 3]]
     dom = max(stages, key=lambda k: stages[k]["ms_per_pair"])
     peak, peak_src = load_peaks()
+    stage_bytes = {"raster": 4 + 4 * S, "shade_mix": 11 * S, "variational_refinement": 10 * S, "cubic_remap": 10 * S, "pyramid_compare": 6 * S,
+                   "triangulate": 16 * S + 4 + 20, "normals": 20 + 28}             # per main-frame pixel, DESIGN.md "Kernels"
     dom_ms_launch = stages[dom]["ms_per_pair"] / max(stages[dom]["launches_per_pair"], 1)
-    dom_bytes_launch = STAGE_ALG_BYTES[dom] * N / max(stages[dom]["launches_per_pair"], 1)
+    dom_bytes_launch = stage_bytes[dom] * N / max(stages[dom]["launches_per_pair"], 1)
     ach = dom_bytes_launch / (dom_ms_launch * 1e-3) / 1e9
-    path_ach = ALG_BYTES_PATH(1) * N * B * K * 1.0 / (ms_res * 1e-3) / 1e9     # per GPU
+    path_bytes_step = ALG_BYTES_PATH(S) * N * B                                     # (33 + 21 S) B per main-frame pixel
+    path_ach = path_bytes_step * K * 1.0 / (ms_res * 1e-3) / 1e9                   # per GPU
 
-    traffic = None
+    prof = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if (W, H) == (1920, 1080) and dom in tj and tj[dom].get("dram_bytes_per_launch"):
-            traffic = tj[dom]["dram_bytes_per_launch"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "kernels_r2.json")))
     except Exception:
         pass
-    pix_total = world * B * K * N
+    same_shape = prof.get("shape") == [W, H, S]
+    traffic = prof.get("dram_bytes_per_main_frame") if same_shape else None
+    clocks = sampler.summary()
+    compute = None
+    if same_shape and prof.get("warp_inst_per_main_frame") and clocks.get("sm_mhz"):
+        # issue-slot roofline: warp instructions of one main frame (ncu smsp__inst_executed.sum of every launch, committed
+        # profile) x main frames per second, against 4 schedulers x 148 SMs x the SM clock sampled in this run
+        inst_rate = prof["warp_inst_per_main_frame"] * B * K / (ms_res * 1e-3)
+        issue_peak = 148 * 4 * clocks["sm_mhz"] * 1e6
+        compute = {"bound": "issue", "achieved": inst_rate / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s", "frac": inst_rate / issue_peak,
+                   "warp_inst_per_main_frame": prof["warp_inst_per_main_frame"], "source": prof.get("source"),
+                   "pipes_pct_of_peak": prof.get("pipes_pct_of_peak"),
+                   "note": "the path reproduces the reference's IEEE arithmetic operation by operation (exact div / sqrt, FP64 islands, 50 Newton "
+                           "iterations, 441-term sequential window sums): every large kernel is issue- or XU/FP64-pipe bound, DRAM throughput is 1-3 %"}
+    pix_total = world * B * K * N * S
     value = pix_total / (ms_res * 1e-3) / 1e6
     e2e_val = pix_total / (ms_e2e * 1e-3) / 1e6
     m_mean = float(counts_dev[(Wm + K - 1) % nbuf].float().mean())
 
+    # ---- host link ceiling: every rank copies device -> pinned host at once for ~0.3 s (outside the timed regions) --------
+    link = None
+    if args.link_probe_s > 0:
+        for r_ in renders:
+            r_.ctx.synchronize()
+        src_rows = rows_dev[0].view(-1)[: N * 7 * min(B, 4)]
+        dst_rows = [rows_pin[0][b].view(-1) for b in range(min(B, 4))]
+        chunk = N * 7
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+        def burst(reps):
+            for i in range(reps):
+                with torch.cuda.stream(streams[i & 1]):
+                    j = i % len(dst_rows)
+                    dst_rows[j].copy_(src_rows[j * chunk:(j + 1) * chunk], non_blocking=True)
+        burst(4)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(8, int(args.link_probe_s * 50e9 / (chunk * 4)))
+        e0.record(torch.cuda.current_stream())
+        for st_ in streams:
+            st_.wait_stream(torch.cuda.current_stream())
+        burst(reps)
+        for st_ in streams:
+            torch.cuda.current_stream().wait_stream(st_)
+        e1.record(torch.cuda.current_stream())
+        barrier()
+        ms_probe = e0.elapsed_time(e1)
+        mine_gbs = reps * chunk * 4 / (ms_probe * 1e-3) / 1e9
+        if world > 1:
+            t = torch.tensor([ms_probe, mine_gbs], dtype=torch.float64, device=dev)
+            allp = torch.empty((world, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allp, t)
+            link = {"aggregate_gbs": world * reps * chunk * 4 / (float(allp[:, 0].max()) * 1e-3) / 1e9, "by_rank_gbs": [round(float(v), 1) for v in allp[:, 1]]}
+        else:
+            link = {"aggregate_gbs": mine_gbs, "by_rank_gbs": [round(mine_gbs, 1)]}
+
+    # ---- exchange content check (N > 1, outside the timed regions): every slot every rank received equals, bit for bit,
+    # what its producer holds; and the compacted rank-ordered cloud (the reference's append order, recon.cpp:115-116)
+    # built from the slots equals the NCCL all-gather of the compacted rows ------------------------------------------------
+    xcheck = None
+    if world > 1:
+        for r_ in renders:
+            r_.ctx.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if use_p2p:
+            from mesh_reconstruction_b200 import shard
+            bad = 0
+            for k_ in range(nbuf):
+                mine_sum = torch.stack([rows_dev[k_].view(torch.int32).sum(dtype=torch.int64), counts_dev[k_].sum(dtype=torch.int64)])
+                allsum = torch.empty((world, 2), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allsum, mine_sum)
+                for p_ in range(world):
+                    got = torch.stack([xch[k_].slot(p_, (B, N, 7)).view(torch.int32).sum(dtype=torch.int64),
+                                       xch[k_].slot(p_, (B,), torch.int32, offset_bytes=rows_bytes).sum(dtype=torch.int64)])
+                    if not torch.equal(got, allsum[p_]):
+                        bad += 1
+            # compacted cloud of the last step from the peer slots vs the torch.distributed all-gather of this rank's compacted rows
+            k_ = (Wm + K + 1) % nbuf                       # buffer set of the last step that ran (the two profiling steps)
+            cnts = torch.stack([xch[k_].slot(p_, (B,), torch.int32, offset_bytes=rows_bytes) for p_ in range(world)]).cpu()
+            cloud = torch.cat([xch[k_].slot(p_, (B, N, 7))[b, :int(cnts[p_, b])] for p_ in range(world) for b in range(B)], 0)
+            own = torch.cat([rows_dev[k_][b, :int(cnts[rank, b])] for b in range(B)], 0)
+            ref_cloud, _ = shard.allgather_points(own, len(own))
+            same = bool(cloud.shape == ref_cloud.shape and torch.equal(cloud.view(torch.int32), ref_cloud.view(torch.int32)))
+            okt = torch.tensor([0 if (bad or not same) else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            xcheck = {"slots_bit_identical_on_every_rank": bool(int(okt.item())), "cloud_rows": int(cloud.shape[0]),
+                      "rank_ordered_cloud_equals_nccl_allgather": same}
+            if not int(okt.item()):
+                raise SystemExit(f"bench.py: rank {rank}: exchanged rows differ from their producer's ({bad} slots) or the compacted cloud differs from the all-gather")
+
     cpu = None
     if rank == 0 and world == 1 and args.cpu_pairs > 0:
+        os.sched_setaffinity(0, affinity0)        # the CPU baseline uses every host core
         cores = os.cpu_count() or 1
-        fr = {i: frames_pin[i].numpy() for i in range(min(n_local, args.cpu_pairs + 1))}
+        n_main = max(1, args.cpu_pairs // S)
+        fr = {i: frames_pin[i].numpy() for i in range(min(n_local, n_main + 2 * (S // 2) + (1 if S == 1 else 0)))}
         sc4 = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err)
         sc4.cameras = cams[idx[0]:idx[0] + len(fr)]
-        prs = [(i, i + 1) for i in range(len(fr) - 1)]
+        lo_, hi_ = main_range(len(fr), S)
+        prs = [(a_, sides_of(a_, S)) for a_ in range(lo_, hi_)][:n_main]
         t, _ = cpu_reference_pairs(sc4, fr, prs, cores, args.farneback)
         import cv2
-        cpu = {"value": len(prs) * N / t / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
-               "sample": f"{len(prs)} frame pairs of {W}x{H} (of the 299-pair workload), cv2 {cv2.__version__} x{cores} threads + C restatement (OpenMP)"}
+        cpu = {"value": len(prs) * S * N / t / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
+               "sample": f"{len(prs)} main frame(s) x {S} side frame(s) of {W}x{H} (of the {args.frames}-frame workload), cv2 {cv2.__version__} x{cores} threads + C restatement (OpenMP)"}
 
     if rank == 0:
+        d2h_step = (N * 28 + 4) * B
+        e2e = {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": (1 + S) * N * B, "d2h_bytes_per_step": d2h_step,   # the DMA moves the full row capacity (count unknown on the host without a sync)
+               "rows_bytes_per_step": int(m_mean * 28 * B), "ms_per_step": ms_e2e / K}
+        if link:
+            # share of the probed host-link ceiling (all ranks copying at once) that the e2e run's row traffic reaches
+            e2e["host_link_gbs"] = link["aggregate_gbs"]
+            e2e["host_link_by_rank_gbs"] = link["by_rank_gbs"]
+            e2e["d2h_achieved_gbs"] = world * d2h_step / (ms_e2e / K * 1e-3) / 1e9
+            e2e["host_link_frac"] = e2e["d2h_achieved_gbs"] / link["aggregate_gbs"]
+            e2e["bound"] = "host link" if e2e["host_link_frac"] > 0.85 else "compute"
         line = {
             "metric": "Mpix/s matched+triangulated", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S=1 (BASELINE config 4)",
-                       "pairs_per_step_per_gpu": B, "contexts_per_gpu": nctx, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_pair": m_mean,
-                       "l2": f"working set per step ({B} pairs x ~{(16 * 4 + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
+            "config": {"workload": workload_name(args), "main_frames_per_step_per_gpu": B, "side_frames": S, "pairs_per_step_per_gpu": B * S,
+                       "contexts_per_gpu": nctx, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_main_frame": m_mean,
+                       "l2": f"working set per step ({B} main frames x ~{((16 * 4 + 24) * S + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
                        "exchange": ("none (single GPU)" if world == 1 else
                                     "copy-engine pushes of rows + counts into every peer's buffer over NVLink (CUDA IPC, mr_xchg_push; no SMs), overlapped with the next step" if use_p2p else
                                     "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step")},
-            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * N * B, "d2h_bytes_per_step": (N * 28 + 4) * B,   # the DMA moves the full row capacity (count unknown on the host without a sync)
-                    "rows_bytes_per_step": int(m_mean * 28 * B),
-                    "ms_per_step": ms_e2e / K},
+            "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "note": "compute-bound stage (IEEE-exact div/sqrt, FP64 islands): HBM fraction is low by construction, see DESIGN.md section 4", "alg_bytes_per_pixel": STAGE_ALG_BYTES[dom],
-                         "ms_per_launch": dom_ms_launch, "launches_per_pair": stages[dom]["launches_per_pair"]},
-            "roofline_path": {"alg_bytes_per_pixel_pair": ALG_BYTES_PATH(1), "achieved": path_ach, "peak": peak, "unit": "GB/s",
-                              "frac": path_ach / peak},
-            "stages_ms_per_pair": {k: round(v["ms_per_pair"], 4) for k, v in stages.items()},
-            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "whole main-frame step (every kernel of the path)", "achieved": path_ach, "peak": peak, "unit": "GB/s",
+                         "frac": path_ach / peak, "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_main_frame_pixel": ALG_BYTES_PATH(S),
+                         "alg_bytes_per_step": path_bytes_step, "ms_per_step": ms_res / K,
+                         "note": "SURVEY 8(d) contract figure (33 + 21 S bytes per main-frame pixel); the path is not HBM-bound, see roofline_compute"},
+            "roofline_kernel": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "alg_bytes_per_pixel": stage_bytes[dom], "ms_per_launch": dom_ms_launch, "launches_per_main_frame": stages[dom]["launches_per_pair"]},
+            "roofline_compute": compute,
+            "stages_ms_per_main_frame": {k: round(v["ms_per_pair"], 4) for k, v in stages.items()},
+            "clocks": clocks,
             "diag": diag_res,      # host time to queue a step; per-rank device time per step (value uses the max)
         }
+        if xcheck:
+            line["exchange_check"] = xcheck
         if cpu:
             line["cpu_baseline"] = cpu
+        try:
+            line["normals_stats"] = dict(zip(["tiles", "tiles_1_sampled_coord", "tiles_2_sampled_coords", "tiles_3_sampled_coords", "residual_pixels"], ctx.normals_stats()))
+        except Exception:
+            pass
         print(json.dumps(line), flush=True)
     if world > 1:
         if use_p2p:
-            # every rank must hold every rank's counts of the last steps (exchange sanity, outside the timed regions)
-            for r_ in renders:
-                r_.ctx.synchronize()
-            torch.cuda.synchronize()
-            dist.barrier()
-            for x in xch:
-                got = torch.stack([x.slot(p, (B,), torch.int32, offset_bytes=rows_bytes) for p in range(world)])
-                if int(got.min()) <= 0:
-                    raise SystemExit(f"bench.py: rank {rank} is missing exchanged counts: {got.tolist()}")
             for x in xch:
                 x.close()
         dist.destroy_process_group()

@@ -27,6 +27,8 @@
 
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -154,6 +156,7 @@ struct IterState {
     int done;            // the reference's loop has ended: later iterations that were already queued do nothing
     int iters;
     int nonfinite;
+    int slow_chunks;     // diagnostics: chunks seqsum added term by term
 };
 
 // score[i] exactly as the reference's scatter loop leaves it (heuristic.cpp:110-124): first the gathered densityTemp of
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(32) chunk_walk_kernel(const float *__restrict_
                 }
             }
             if (!fast) {
+                if (lane == 0 && st) atomicAdd((int *)&st->slow_chunks, 1);
                 const long long base = (long long)(c0 + k) * CH;
                 for (int q = lane; q < CH; q += 32) buf[q] = base + q < n ? terms[base + q] : 0.f;
                 __syncwarp();
@@ -487,6 +491,28 @@ __global__ void gather_kernel(int n, const int *__restrict__ flag, const int *__
 
 #define FL_LAUNCH(ctx, name) MR_LAUNCH_CHECK(ctx, name)
 
+// MR_FILTER_TIMING=1: phase times on stderr (synchronises; diagnostics only)
+struct PhaseTimer {
+    mr_context *ctx;
+    bool on;
+    cudaEvent_t a, b;
+    PhaseTimer(mr_context *c) : ctx(c), on(getenv("MR_FILTER_TIMING") != nullptr)
+    {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream); }
+    }
+    void lap(const char *what)
+    {
+        if (!on) return;
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "[mr_filter] %-28s %9.3f ms\n", what, ms);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~PhaseTimer() { if (on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
+
 int seqsum(mr_context *ctx, const float *terms, long long n, double *d_out, const IterState *st, double *csum, int *cexp, IncMap *cmap, int *nonfinite)
 {
     const int nchunks = (int)((n + CH - 1) / CH);
@@ -557,6 +583,7 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
     int *sidx = cidx + n, *cntL = cnt, *cntU = cnt + n;
     long long *offL = off, *offU = off + (n + 1);
 
+    PhaseTimer tm(ctx);
     dehom_kernel<<<G, T, 0, st>>>(d_pts, pstride, n, p3);
     FL_LAUNCH(ctx, "dehom_kernel");
     // cell edge a little above the Euclidean radius (`radius` bounds SQUARED distances); the grid only narrows the
@@ -571,6 +598,7 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
         neighbour_kernel<false><<<cdiv(n, 128), 128, 0, st>>>(p3, skey, sidx, n, inv_cell, radius, cntL, cntU, nullptr, nullptr, nullptr, nullptr);
         FL_LAUNCH(ctx, "neighbour_kernel<count>");
     }
+    tm.lap("cells + neighbour count");
     MR_CUDA(ctx, cudaMemsetAsync(off, 0, 2 * ((size_t)n + 1) * sizeof(long long), st));
     CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntL, offL + 1, n, st));
     CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntU, offU + 1, n, st));
@@ -599,6 +627,7 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
         unpack_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keyL + Ea, keyU + Ea, E, radius, nbL, wL, nbU, wU);
         FL_LAUNCH(ctx, "unpack_edges_kernel");
     }
+    tm.lap("neighbour table (fill + sort)");
     // ---- power iteration ------------------------------------------------------------------------------------------
     fill_kernel<<<G, T, 0, st>>>(n, 1.f, density);                            // std::vector<float> density(pointCount, 1.)
     FL_LAUNCH(ctx, "fill_kernel");
@@ -624,8 +653,10 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
         MR_CUDA(ctx, cudaStreamSynchronize(st));
         h_done = h.done;
         h_iters = h.iters;
+        if (tm.on) fprintf(stderr, "[mr_filter] iterations %d, slow chunks so far %d\n", h.iters, h.slow_chunks);
     }
     if (info) info[1] = h_iters;
+    tm.lap("power iteration");
     // ---- thinning -----------------------------------------------------------------------------------------------------
     int *rank = mr_buf<int>(ctx, "fl_rank", (size_t)n), *state = mr_buf<int>(ctx, "fl_state", (size_t)n);
     int *work = mr_buf<int>(ctx, "fl_work", 2 * (size_t)n), *nwork = mr_buf<int>(ctx, "fl_nwork", 2);
@@ -659,6 +690,7 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
         cur ^= 1;
     }
     if (info) info[2] = rounds;
+    tm.lap("thinning");
     // ---- compaction, ascending index (heuristic.cpp:165-175) -------------------------------------------------------------
     int *flag = cntL, *pos = cntU;
     keep_flag_kernel<<<G, T, 0, st>>>(n, state, flag);
@@ -668,5 +700,6 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
     FL_LAUNCH(ctx, "gather_kernel");
     MR_CUDA(ctx, cudaMemcpyAsync(h_count, nwork, sizeof(int), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));
+    tm.lap("compaction");
     return MR_OK;
 }
