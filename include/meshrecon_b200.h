@@ -178,6 +178,20 @@ int mr_xchg_open(mr_context *ctx, const unsigned char ipc_handle[64], void **pee
 int mr_xchg_close(mr_context *ctx, void *peer_ptr);
 int mr_xchg_push(mr_context *ctx, void *peer_dst, const void *src, size_t bytes);
 void *mr_xchg_stream(mr_context *ctx);
+/* ---- frame ingest  configuration.cpp:226-245 -------------------------------------------------------
+ * What Configuration does to every decoded frame before the path sees it: cv::resize(frame, Size(width, height),
+ * CV_INTER_AREA) when the clip is larger than the render size (the -s scaling factor), then cv::cvtColor(CV_BGR2GRAY).
+ * bgr: src_height x src_width x 3 uint8 (host -- ideally a pinned ring buffer the decoder writes into -- or device);
+ * the frame must be the context's size times ONE integer factor (the reference warns about anything else);
+ * out_gray: H x W uint8, host or device (pass the device frame buffer mr_process_main_frame will read).  Arithmetic is
+ * OpenCV's (integer box sums + its rounding, fixed-point gray), bit-identical to the cv2 binary.  Video decoding and
+ * estimateExposure (off by default, configuration.cpp:25) stay on the host.  Asynchronous for device outputs
+ * (enqueued on mr_stream); a host input must stay untouched until the stream has drained. */
+int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, uint8_t *out_gray);
+/* BGR2GRAY coefficients: 15 (default) = the 15-bit ones of OpenCV >= 3.4.6 / 4.x (3735, 19235, 9798), 14 = the 14-bit
+ * ones of OpenCV 3.0 - 3.4.5 (1868, 9617, 4899) -- the reference does not pin its OpenCV version (Makefile:10). */
+int mr_set_gray_shift(mr_context *ctx, int shift);
+
 /* ---- Heuristic::filterPoints  heuristic.cpp:55-176 ------------------------------------------------
  * The step that consumes the gathered cloud after every pass over the main frames (recon.cpp:125): outlier / redundancy
  * filter by local density -- radius-neighbour table restricted to j < i, clamped power iteration (up to 200 sweeps),

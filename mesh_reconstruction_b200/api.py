@@ -95,6 +95,8 @@ def load_library():
     L.mr_profile_enable.argtypes = [vp, C.c_int]
     L.mr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.mr_normals_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mr_ingest_frame.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.mr_set_gray_shift.argtypes = [vp, C.c_int]
     L.mr_filter_points.argtypes = [vp, vp, vp, C.c_size_t, C.c_float, vp, vp, vp, C.POINTER(C.c_size_t)]
     L.mr_filter_rows.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, vp, C.POINTER(C.c_size_t)]
     L.mr_filter_info.argtypes = [vp, C.POINTER(C.c_longlong), vp, vp]
@@ -443,3 +445,16 @@ def filter_info(ctx, want_arrays=False, n=None):
         return {"n_edges": info[0], "iters": info[1], "rounds": info[2], "density": density, "score": score}
     ctx.check(ctx.lib.mr_filter_info(ctx.h, info, None, None))
     return {"n_edges": info[0], "iters": info[1], "rounds": info[2]}
+
+
+def ingest_frame(ctx, bgr, out=None):
+    """``mr_ingest_frame``: what configuration.cpp:226-245 does to a decoded frame -- ``cv::resize(INTER_AREA)`` to the
+    context's size when the frame is an integer multiple of it, then ``cv::cvtColor(BGR2GRAY)``.  ``bgr``: h x w x 3 uint8
+    (NumPy / pinned or CUDA tensor); returns the H x W gray frame (NumPy, or ``out`` -- e.g. a CUDA tensor)."""
+    h, w = int(bgr.shape[0]), int(bgr.shape[1])
+    pb, kb = _ptr(bgr, np.uint8)
+    if out is None:
+        out = np.empty((ctx.H, ctx.W), np.uint8)
+    po, ko = _ptr(out, np.uint8)
+    ctx.check(ctx.lib.mr_ingest_frame(ctx.h, pb, w, h, po))
+    return out

@@ -817,6 +817,36 @@ int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9])
     return MR_OK;
 }
 
+// Frame ingest of Configuration::Configuration (configuration.cpp:226-245): BGR frame -> (INTER_AREA shrink) -> gray.
+int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, uint8_t *out_gray)
+{
+    CHECK_CTX(ctx);
+    SET_DEVICE(ctx);
+    CHECK_ARG(ctx, bgr && out_gray, "null argument");
+    CHECK_ARG(ctx, src_width >= ctx->W && src_height >= ctx->H && src_width % ctx->W == 0 && src_height % ctx->H == 0 &&
+                       src_width / ctx->W == src_height / ctx->H,
+              "the frame must be the render size times one integer factor in both directions (configuration.cpp:149-151)");
+    const size_t in_bytes = (size_t)src_width * src_height * 3;
+    const uint8_t *d_in = (const uint8_t *)mr_in(ctx, bgr, in_bytes, "in_bgr");
+    const bool dev_out = mr_is_device_ptr(out_gray);
+    uint8_t *d_out = dev_out ? out_gray : mr_buf<uint8_t>(ctx, "ingest_gray", ctx->N);
+    if (!d_in || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_ingest_frame", "alloc");
+    RC(k_ingest(ctx, d_in, src_width, src_height, d_out));
+    if (!dev_out) {
+        RC(mr_out(ctx, out_gray, d_out, ctx->N));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_set_gray_shift(mr_context *ctx, int shift)
+{
+    CHECK_CTX(ctx);
+    CHECK_ARG(ctx, shift == 14 || shift == 15, "shift must be 14 (OpenCV 3.0-3.4.5) or 15 (OpenCV >= 3.4.6 / 4.x)");
+    ctx->gray_shift = shift;
+    return MR_OK;
+}
+
 // Heuristic::filterPoints (heuristic.cpp:55-176) on the device.  points: n x 4 (stride ps floats), normals: n x 3 (stride ns) or
 // null; host or device memory (host inputs are staged).  Outputs likewise; out_points / out_normals / out_keep may be null.
 static int filter_impl(mr_context *ctx, const float *points, int ps, const float *normals, int ns, size_t n, float radius, float *out_points,

@@ -58,6 +58,7 @@ struct mr_context {
     // mesh (Render::loadMesh)
     int F = 0;
     bool mesh_loaded = false;                    // a successful mr_load_mesh happened (render calls give MR_ENOMESH otherwise)
+    int gray_shift = 15;                         // mr_set_gray_shift: BGR2GRAY fixed-point coefficients (15: OpenCV >= 3.4.6 / 4.x, 14: older 3.x)
     bool use_farneback = false;   // mr_set_use_farneback: the reference's -f switch for mr_process_main_frame
     // last results
     int last_count = 0;
@@ -189,6 +190,8 @@ int k_flow_remap(mr_context *ctx, const float *d_flow, int stride_floats, const 
 int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_out, int out_stride, int out_off);
 int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4);   // farneback.cu
 int mr_flow_init_tables(mr_context *ctx);
+// ingest.cu
+int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray);
 // filter.cu
 int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const float *d_nrm, int nstride, int n, float radius, float *d_out_pts,
                     int opstride, float *d_out_nrm, int onstride, int *d_out_keep, int *h_count, long long *info);

@@ -1,0 +1,81 @@
+// ingest.cu -- frame ingest of Configuration::Configuration (configuration.cpp:226-245), the step right before the hot
+// path: every decoded BGR frame is (optionally) shrunk to the render size with
+// cv::resize(..., CV_INTER_AREA) and turned into the gray frame the path works on (cv::cvtColor CV_BGR2GRAY).  Video
+// DECODING stays on the host (cv::VideoCapture / FFmpeg, no NVDEC library in this image); what moves to the GPU is the
+// per-pixel work, so that a decoded frame crosses PCIe once (3 B/px, or 3 f^2 B per output pixel when shrinking) and
+// the gray frame is born in HBM, where mr_process_main_frame wants it.
+//
+// Arithmetic = OpenCV's, checked against the cv2 binary (tests/test_gpu_ingest.py):
+//   * INTER_AREA with an integer factor f (the reference warns about anything else, configuration.cpp:149-151) is
+//     OpenCV's resizeAreaFast_: integer box sum, then  f == 2: (sum + 2) >> 2 ;  otherwise
+//     saturate_cast<uchar>(sum * (float)(1 / f^2)) (float product, round half to even).
+//   * BGR2GRAY 8U: (B * BY + G * GY + R * RY + half) >> shift with the 15-bit coefficients (3735, 19235, 9798) of
+//     OpenCV >= 3.4.6 / 4.x (the cv2 binary the oracle is pinned to) or the 14-bit ones (1868, 9617, 4899) of
+//     OpenCV 3.0 - 3.4.5 (mr_set_gray_shift).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r, int shift)
+{
+    if (shift == 15) return (b * 3735u + g * 19235u + r * 9798u + (1u << 14)) >> 15;
+    return (b * 1868u + g * 9617u + r * 4899u + (1u << 13)) >> 14;
+}
+
+// factor 1: four pixels per thread (12 bytes in as three 32-bit words when aligned, one 32-bit word out)
+__global__ void __launch_bounds__(256) gray_kernel(const uint8_t *__restrict__ bgr, size_t n, int shift, uint8_t *__restrict__ out)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // group of 4 pixels
+    const size_t p0 = q * 4;
+    if (p0 >= n) return;
+    if (p0 + 4 <= n && ((uintptr_t)bgr & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(bgr) + q * 3;
+        const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+        // bytes: a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3
+        const unsigned g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255, shift);
+        const unsigned g1 = gray_of(a >> 24, b & 255, (b >> 8) & 255, shift);
+        const unsigned g2 = gray_of((b >> 16) & 255, b >> 24, c & 255, shift);
+        const unsigned g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24, shift);
+        reinterpret_cast<uint32_t *>(out)[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        return;
+    }
+    for (size_t p = p0; p < n && p < p0 + 4; p++) out[p] = (uint8_t)gray_of(bgr[3 * p], bgr[3 * p + 1], bgr[3 * p + 2], shift);
+}
+
+// factor f >= 2: one thread per output pixel, box sums of the three channels, OpenCV's rounding, then gray
+__global__ void __launch_bounds__(256) area_gray_kernel(const uint8_t *__restrict__ bgr, int sw, int W, int H, int f, int shift, uint8_t *__restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    unsigned s0 = 0, s1 = 0, s2 = 0;
+    for (int dy = 0; dy < f; dy++) {
+        const uint8_t *row = bgr + ((size_t)(y * f + dy) * sw + (size_t)x * f) * 3;
+        for (int dx = 0; dx < f; dx++) { s0 += row[3 * dx]; s1 += row[3 * dx + 1]; s2 += row[3 * dx + 2]; }
+    }
+    unsigned b, g, r;
+    if (f == 2) { b = (s0 + 2) >> 2; g = (s1 + 2) >> 2; r = (s2 + 2) >> 2; }
+    else {
+        const float scale = 1.f / (float)(f * f);
+        b = (unsigned)__float2int_rn((float)s0 * scale); g = (unsigned)__float2int_rn((float)s1 * scale); r = (unsigned)__float2int_rn((float)s2 * scale);
+        b = min(b, 255u); g = min(g, 255u); r = min(r, 255u);
+    }
+    out[(size_t)y * W + x] = (uint8_t)gray_of(b, g, r, shift);
+}
+
+}  // namespace
+
+int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray)
+{
+    const int W = ctx->W, H = ctx->H;
+    if (src_w == W && src_h == H) {
+        const size_t groups = (ctx->N + 3) / 4;
+        gray_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, ctx->stream>>>(d_bgr, ctx->N, ctx->gray_shift, d_gray);
+        MR_LAUNCH_CHECK(ctx, "gray_kernel");
+        return MR_OK;
+    }
+    const int f = src_w / W;
+    dim3 b(32, 8), g(cdiv(W, 32), cdiv(H, 8));
+    area_gray_kernel<<<g, b, 0, ctx->stream>>>(d_bgr, src_w, W, H, f, ctx->gray_shift, d_gray);
+    MR_LAUNCH_CHECK(ctx, "area_gray_kernel");
+    return MR_OK;
+}

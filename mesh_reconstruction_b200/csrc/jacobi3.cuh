@@ -7,7 +7,7 @@
 // two indices: indR[0] in {1,2} and indC[2] in {0,1} (indR[1] == 2 and indC[1] == 0 always).  They are
 // refreshed only for the rows/columns of the last rotation, i.e. one of them may be STALE -- that is part
 // of the reference behaviour (it decides which off-diagonal is zeroed next) and is reproduced here.
-// hypot() is evaluated through double (correctly rounded float), see tri.cu.
+// hypot() is OpenCV's own float formula (not libm's), see mr_hypot_f.
 #pragma once
 #include <math.h>
 
@@ -17,7 +17,16 @@
 #define MR_HD static inline
 #endif
 
-MR_HD float mr_hypot_f(float a, float b) { return (float)sqrt((double)a * (double)a + (double)b * (double)b); }
+// OpenCV's own hypot (lapack.cpp, used by JacobiImpl_ instead of libm's): float arithmetic scaled by the larger
+// operand.  Pinned bit for bit against cv2.eigen / cv2.PCACompute2 (tests/test_oracle_cv.py).
+MR_HD float mr_hypot_f(float a, float b)
+{
+    a = fabsf(a);
+    b = fabsf(b);
+    if (a > b) { b = b / a; return a * sqrtf(1.f + b * b); }
+    if (b > 0.f) { a = a / b; return b * sqrtf(1.f + a * a); }
+    return 0.f;
+}
 
 // cov: c00, c01, c02, c11, c12, c22.  W: eigenvalues (descending), V: eigenvectors in rows.
 MR_HD void mr_jacobi3(const float *cov6, float *Wout, float *Vout)

@@ -598,6 +598,15 @@ void orc_camera_center(const float *P, float *c3)
 /* cv::eigen on a symmetric 3x3 CV_32F matrix (Jacobi, OpenCV JacobiImpl_).   */
 /* W: eigenvalues descending, V: eigenvectors in rows.                        */
 /* ------------------------------------------------------------------------ */
+/* OpenCV's own hypot of lapack.cpp (JacobiImpl_ does not call libm's): float arithmetic, scaled by the larger operand */
+static float cv_hypotf(float a, float b)
+{
+    a = fabsf(a); b = fabsf(b);
+    if (a > b) { b /= a; return a * sqrtf(1 + b * b); }
+    if (b > 0) { a /= b; return b * sqrtf(1 + a * a); }
+    return 0;
+}
+
 void orc_jacobi3(float *A, float *W, float *V)
 {
     const int n = 3;
@@ -635,8 +644,8 @@ void orc_jacobi3(float *A, float *W, float *V)
         float p = A[n * k + l];
         if (fabsf(p) <= eps) break;
         float y = (float)((W[l] - W[k]) * 0.5);
-        float t = fabsf(y) + hypotf(p, y);
-        float s = hypotf(p, t);
+        float t = fabsf(y) + cv_hypotf(p, y);
+        float s = cv_hypotf(p, t);
         float c = t / s;
         s = p / s; t = (p / t) * p;
         if (y < 0) s = -s, t = -t;

@@ -135,7 +135,6 @@ def test_register_jacobi_equals_opencv_jacobi():
         w2, v2 = np.empty(3, np.float32), np.empty(9, np.float32)
         L.orc_jacobi3(a, w2, v2)
         nbit += int(np.array_equal(w, w2) and np.array_equal(v, v2))
-        assert np.allclose(w, w2, rtol=1e-5, atol=1e-12) and np.allclose(np.abs(v), np.abs(v2), atol=2e-3)
-    assert nbit >= 2990          # bit-identical except where glibc's hypotf is not correctly rounded
-    ok, evals, evecs = cv2.eigen(cov)
-    assert np.allclose(evals.ravel(), w, rtol=1e-4, atol=1e-10)
+        ok, evals, evecs = cv2.eigen(cov)                      # the OpenCV binary itself
+        assert np.array_equal(evals.ravel(), w) and np.array_equal(evecs.ravel(), v), t
+    assert nbit == 3000          # and bit-identical to the oracle's generic restatement

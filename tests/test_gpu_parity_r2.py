@@ -222,3 +222,18 @@ def test_load_mesh_rejects_out_of_range_indices():
     d = r.depth(sc.cameras[0])
     assert (d != 1.0).any()
     assert ctx.lib.mr_load_mesh(ctx.h, None, 0, C.c_void_p(sc.faces.ctypes.data), 3) == -1
+
+
+def test_cuda_reproduces_cv2_transliteration(golden_dir):
+    """The CUDA triangulatePixels against the output of the cv2-level transliteration of util.cpp:62-329 (every cv::Mat
+    expression evaluated by the OpenCV binary, tests/golden/make_cv2_transliteration.py): whole rows bit-identical, for
+    S = 2 and for the S = 1 case with isolated pixels (K < 3) and a zero-variance pixel (NaN row)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "scene_s2_96x72.npz"))
+    t = np.load(os.path.join(golden_dir, "cv2_translit_s2_96x72.npz"))
+    fa, sides = int(g["fa"]), [int(s) for s in g["sides"]]
+    cams = g["cameras"]
+    got = mr.triangulatePixels(list(g["flows"]), cams[fa], [cams[s] for s in sides], g["depth"])
+    assert _same(got, t["tri"])
+    got1 = mr.triangulatePixels([t["flow1"]], cams[fa], [cams[sides[0]]], t["depth1"])
+    assert np.isnan(t["tri1"]).any() and _same(got1, t["tri1"])

@@ -101,7 +101,8 @@ def test_small_linalg_bit_exact():
 
 
 def test_pca_matches_cv2():
-    """orc_pca_normal restates cv::PCA + cv::eigen (Jacobi); compare to cv2.PCACompute2."""
+    """orc_pca_normal restates cv::PCA (cv::reduce mean, cv::mulTransposed covariance, cv::eigen = JacobiImpl_ with
+    OpenCV's own hypot): BIT-IDENTICAL to cv2.PCACompute2 -- smallest eigenvector and all eigenvalues."""
     rng = np.random.default_rng(4)
     L = native.lib()
     worst = 0.0
@@ -114,10 +115,12 @@ def test_pca_matches_cv2():
         n = np.empty(3, f32)
         ev = np.empty(3, f32)
         L.orc_pca_normal(np.ascontiguousarray(pts), K, n, ev)
-        c = abs(float(np.dot(n.astype(np.float64), evec[2].astype(np.float64))))
-        worst = max(worst, 1 - c)
-        assert np.allclose(ev, evals.ravel(), rtol=2e-3, atol=1e-9)
-    assert worst < 1e-5
+        assert np.array_equal(n, evec[2]), (t, K, n, evec[2])
+        assert np.array_equal(ev, evals.ravel()), (t, K, ev, evals.ravel())
+        # and stage by stage: mean (cv::reduce), covariance (cv::calcCovarMatrix -> mulTransposed)
+        cov, mean2 = cv2.calcCovarMatrix(pts, None, cv2.COVAR_NORMAL | cv2.COVAR_SCALE | cv2.COVAR_ROWS, ctype=cv2.CV_32F)
+        assert np.array_equal(mean2.ravel().astype(f32), mean.ravel())
+    assert worst == 0.0
 
 
 def test_camera_center_matches_decompose_and_yaml_convention():
