@@ -307,23 +307,37 @@ __device__ __forceinline__ void finish_tile(Smem &s, const TileInfo &ti, const i
         }
         store_covk(out + (size_t)(by + ly0 + j) * W + bx + vx, ti, covp, K[j]);
     }
-    if (NF >= 1 && residual) {
-        // rare: a partial sum of the reference's double accumulation is not exactly representable -> take its own loop
-#pragma unroll 1
-        for (int j = 0; j < VR; j++) {
-            if (!(residual & (1u << j))) continue;
-            const float mj[3] = {j == 0 ? mf[0][0] : (j == 1 ? mf[1][0] : mf[2][0]), j == 0 ? mf[0][1] : (j == 1 ? mf[1][1] : mf[2][1]),
-                                 j == 0 ? mf[0][2] : (j == 1 ? mf[1][2] : mf[2][2])};
-            const int Kj = j == 0 ? K[0] : (j == 1 ? K[1] : K[2]);
+    if (NF >= 1) {
+        // Rare: a partial sum of the reference's double accumulation is not exactly representable -> take its own loop.
+        // The block's residual pixels are gathered into one list first, so that they fill whole warps instead of
+        // keeping every warp that owns one of them busy for a full window walk.
+        __shared__ int s_nres;
+        __shared__ unsigned s_res[TX * TY];          // ly << 8 | lx
+        if (tid == 0) s_nres = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < VR; j++)
+            if (residual & (1u << j)) s_res[atomicAdd(&s_nres, 1)] = (unsigned)((ly0 + j) << 8) | (unsigned)vx;
+        __syncthreads();
+        const int nres = s_nres;
+        for (int r = tid; r < nres; r += NT) {
+            const int ly = (int)(s_res[r] >> 8), lx = (int)(s_res[r] & 255u);
+            // K of that pixel again (cheap next to the window walk) from the valid flags; its window sums from s.mean
+            int Kj = 0;
+            for (int dy = 0; dy < WIN; dy++)
+                for (int dx = 0; dx < WIN; dx++) Kj += s.tile[ly + dy][lx + dx].w != 0.f;
+            const float sK = rcpf_d((float)Kj);
+            const float4 ms = s.mean[ly][lx];
+            const float mj[3] = {ms.x * sK, ms.y * sK, ms.z * sK};
             double a6[6];
-            residual_cov(s, ti, n_int, ly0 + j, vx, mj, a6);
+            residual_cov(s, ti, n_int, ly, lx, mj, a6);
             const double scale = 1.0 / (double)Kj;
             float covp[6];
 #pragma unroll
             for (int q = 0; q < 6; q++) covp[q] = (float)(a6[q] * scale);
-            store_covk(out + (size_t)(by + ly0 + j) * W + bx + vx, ti, covp, Kj);
-            if (stats) atomicAdd(stats + 4, 1ull);
+            store_covk(out + (size_t)(by + ly) * W + bx + lx, ti, covp, Kj);
         }
+        if (tid == 0 && nres && stats) atomicAdd(stats + 4, (unsigned long long)nres);
     }
 }
 
