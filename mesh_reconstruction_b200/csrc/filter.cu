@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(32) chunk_walk_kernel(const float *__restrict_
                                                         const IterState *__restrict__ st)
 {
     if (st && st->done) return;
-    __shared__ float buf[CH];
+    __shared__ float buf[CH + 32];          // 32 sub-chunks of 64 terms at a pitch of 65 (conflict-free lane-private walks)
     const int lane = threadIdx.x;
     double s = 0.0;
     if (*nonfinite) {
@@ -358,6 +358,29 @@ __global__ void __launch_bounds__(32) chunk_walk_kernel(const float *__restrict_
         IncMap m_l;
         m_l.i0 = m_l.i1 = 0;
         if (c < nchunks && e_l != INT_MIN) m_l = cmap[c];
+        {
+            // common case: the 32 chunks of this group all sit in the binade of the running sum -> compose their maps
+            // with an ordered shuffle tree and apply the composite in one step
+            const long long bits = __double_as_longlong(s);
+            const int es = (int)((bits >> 52) & 0x7ff) - 1023;
+            const int e_mine = c < nchunks ? e_l : es;          // lanes past the end: identity map in the same binade
+            if (s > 0.0 && __all_sync(0xffffffffu, e_mine == es && e_mine != INT_MIN)) {
+                IncMap t = m_l;
+                for (int d = 1; d < 32; d <<= 1) {
+                    IncMap r;
+                    r.i0 = __shfl_down_sync(0xffffffffu, t.i0, d);
+                    r.i1 = __shfl_down_sync(0xffffffffu, t.i1, d);
+                    if ((lane % (2 * d)) == 0) t = compose(t, r);
+                }
+                const long long g0 = __shfl_sync(0xffffffffu, t.i0, 0), g1 = __shfl_sync(0xffffffffu, t.i1, 0);
+                const long long mant = (bits & 0xfffffffffffffll) | (1ll << 52);
+                const long long m2 = mant + ((mant & 1) ? g1 : g0);
+                if (m2 < (1ll << 53)) {
+                    s = __longlong_as_double((bits & ~0xfffffffffffffll) | (m2 & 0xfffffffffffffll));
+                    continue;
+                }
+            }
+        }
         for (int k = 0; k < 32 && c0 + k < nchunks; k++) {
             const int e = __shfl_sync(0xffffffffu, e_l, k);
             const long long i0 = __shfl_sync(0xffffffffu, m_l.i0, k), i1 = __shfl_sync(0xffffffffu, m_l.i1, k);
@@ -374,16 +397,54 @@ __global__ void __launch_bounds__(32) chunk_walk_kernel(const float *__restrict_
                 }
             }
             if (!fast) {
+                // The running sum may cross a power of two inside this chunk.  Same idea one level down: 32 sub-chunks of
+                // 64 terms, one per lane -- approximate prefix inside the chunk, exponent per sub-chunk, increment maps for
+                // the stable ones (computed by all lanes at once), then the lanes are visited in order and only the
+                // sub-chunk(s) that really contain the crossing are added term by term.
                 if (lane == 0 && st) atomicAdd((int *)&st->slow_chunks, 1);
+                constexpr int SUB = CH / 32;
                 const long long base = (long long)(c0 + k) * CH;
-                for (int q = lane; q < CH; q += 32) buf[q] = base + q < n ? terms[base + q] : 0.f;
+                for (int q = lane; q < CH; q += 32) buf[(q / SUB) * (SUB + 1) + q % SUB] = base + q < n ? terms[base + q] : 0.f;
                 __syncwarp();
-                if (lane == 0) {
-                    double a = s;
-                    for (int q = 0; q < CH; q++) a += (double)buf[q];
-                    s = a;
+                const float *mine = buf + lane * (SUB + 1);
+                double part = 0.0;
+                for (int q = 0; q < SUB; q++) part += (double)mine[q];
+                double incl = part;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
                 }
-                s = __shfl_sync(0xffffffffu, s, 0);
+                const double lo = (s + (incl - part)) * (1.0 - 9.5367431640625e-07), hi = (s + incl) * (1.0 + 9.5367431640625e-07);
+                int e2 = INT_MIN;
+                if (lo > 0.0) {
+                    const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff), ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff);
+                    if (elo == ehi && elo > 0 && elo < 0x7ff) e2 = elo - 1023;
+                }
+                IncMap m2;
+                m2.i0 = m2.i1 = 0;
+                if (e2 != INT_MIN)
+                    for (int q = 0; q < SUB; q++) m2 = compose(m2, term_map(mine[q], e2));
+                for (int l = 0; l < 32; l++) {
+                    const int el = __shfl_sync(0xffffffffu, e2, l);
+                    const long long j0 = __shfl_sync(0xffffffffu, m2.i0, l), j1 = __shfl_sync(0xffffffffu, m2.i1, l);
+                    const long long b2 = __double_as_longlong(s);
+                    const int es2 = (int)((b2 >> 52) & 0x7ff) - 1023;
+                    bool ok2 = false;
+                    if (el != INT_MIN && es2 == el && s > 0.0) {
+                        const long long mant = (b2 & 0xfffffffffffffll) | (1ll << 52);
+                        const long long mm = mant + ((mant & 1) ? j1 : j0);
+                        if (mm < (1ll << 53)) {
+                            s = __longlong_as_double((b2 & ~0xfffffffffffffll) | (mm & 0xfffffffffffffll));
+                            ok2 = true;
+                        }
+                    }
+                    if (!ok2) {
+                        double a = s;
+                        if (lane == l)
+                            for (int q = 0; q < SUB; q++) a += (double)mine[q];
+                        s = __shfl_sync(0xffffffffu, a, l);
+                    }
+                }
                 __syncwarp();
             }
         }

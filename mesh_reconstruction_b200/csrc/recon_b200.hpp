@@ -17,6 +17,7 @@
 #include <cstring>
 #include <list>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -60,22 +61,17 @@ inline void check(mr_context *ctx, int rc)
 {
     if (rc != MR_OK) throw Error(rc, mr_last_error(ctx));
 }
-// one context per (device, width, height), shared by Render and the free functions
-inline mr_context *&slot(int device, int w, int h)
-{
-    struct Key { int d, w, h; mr_context *c; };
-    static std::vector<Key> all;
-    for (auto &k : all) if (k.d == device && k.w == w && k.h == h) return k.c;
-    all.push_back({device, w, h, nullptr});
-    return all.back().c;
-}
+// one context per (thread, device, width, height), shared by Render and the free functions: calls on a context are
+// serialised by its owner (meshrecon_b200.h), so every host thread gets its own
 inline mr_context *ctx_for(int w, int h, int device = 0)
 {
-    mr_context *&c = slot(device, w, h);
-    if (!c) {
-        int rc = mr_create(&c, device, w, h);
-        if (rc != MR_OK) throw Error(rc, mr_last_error(nullptr));
-    }
+    struct Key { int d, w, h; mr_context *c; };
+    thread_local std::vector<Key> mine;
+    for (auto &k : mine) if (k.d == device && k.w == w && k.h == h) return k.c;
+    mr_context *c = nullptr;
+    int rc = mr_create(&c, device, w, h);
+    if (rc != MR_OK) throw Error(rc, mr_last_error(nullptr));
+    mine.push_back({device, w, h, c});
     return c;
 }
 }  // namespace detail
@@ -182,6 +178,35 @@ inline Mat triangulatePixels(const MatList flows, const Mat mainCamera, const Ma
                                            all.ptr<float>(), &count));
     Mat out(count, 7, F32, 1);  // "points.resize(pixelId)" util.cpp:248
     if (count) std::memcpy(out.data(), all.data(), (size_t)count * 7 * sizeof(float));
+    return out;
+}
+
+
+// == heuristic.cpp ==  void Heuristic::filterPoints(Mat& points, Mat& normals)   recon.hpp:115, heuristic.cpp:55-176
+// `radius` is the alphaVals.back() / 4 the reference derives from its alpha shape (heuristic.cpp:63); like there it
+// bounds SQUARED distances.  points (n x 4) and normals (n x 3) are replaced by the survivors, in ascending index order.
+inline void filterPoints(Mat &points, Mat &normals, float radius, int device = 0)
+{
+    assert(points.cols == 4 && normals.cols == 3 && points.rows == normals.rows);
+    mr_context *c = detail::ctx_for(16, 16, device);           // the filter does not depend on the render size
+    Mat op(points.rows ? points.rows : 1, 4, F32), on(points.rows ? points.rows : 1, 3, F32);
+    size_t m = 0;
+    detail::check(c, mr_filter_points(c, points.ptr<float>(), normals.ptr<float>(), (size_t)points.rows, radius, op.ptr<float>(), on.ptr<float>(),
+                                      nullptr, &m));
+    Mat p2((int)m, 4, F32), n2((int)m, 3, F32);                // points.resize(writeIndex)  heuristic.cpp:174-175
+    if (m) { std::memcpy(p2.data(), op.data(), m * 16); std::memcpy(n2.data(), on.data(), m * 12); }
+    points = p2;
+    normals = n2;
+}
+
+// == configuration.cpp:226-245 ==  what Configuration does to every decoded frame: cv::resize(INTER_AREA) to the render
+// size (integer factor) + cv::cvtColor(CV_BGR2GRAY)
+inline Mat ingestFrame(const Mat bgr, int width, int height, int device = 0)
+{
+    assert(bgr.channels() == 3 && bgr.depth == U8);
+    mr_context *c = detail::ctx_for(width, height, device);
+    Mat out(height, width, U8, 1);
+    detail::check(c, mr_ingest_frame(c, bgr.ptr<uint8_t>(), bgr.cols, bgr.rows, out.ptr<uint8_t>()));
     return out;
 }
 

@@ -3,10 +3,12 @@
 // them with the oracle.  Usage: host_mirror_test <in.bin> <out.bin>
 //   in.bin : int32 W,H,V,F,S | V*4 f32 vertices | F*3 i32 faces | 16 f32 main cam | S*16 f32 side cams
 //            | W*H u8 main frame | S * W*H u8 side frames
-//   out.bin: int32 M | M*7 f32 rows
+//   out.bin: int32 M | M*7 f32 rows | int32 K | K*4 f32 filtered points | K*3 f32 filtered normals
+//            (hint.filterPoints(points, normals) of recon.cpp:125 with radius = (bbox diagonal / 100)^2)
 // Without a GPU it must fail loudly (exit code 3, message on stderr) -- there is no CPU fallback.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../mesh_reconstruction_b200/csrc/recon_b200.hpp"
@@ -49,12 +51,33 @@ int main(int argc, char **argv)
         }
         Mat tri = triangulatePixels(flows, mainCam, cameras, depth);         // recon.cpp:114
         delete render;
-        FILE *o = fopen(argv[2], "wb");
+        // recon.cpp:115-116,125: points / normals of the cloud, then hint.filterPoints(points, normals)
         int32_t M = tri.rows;
+        Mat points(M, 4, F32), normals(M, 3, F32);
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int i = 0; i < M; i++) {
+            const float *r = tri.ptr<float>(i);
+            std::memcpy(points.ptr<float>(i), r, 16);
+            std::memcpy(normals.ptr<float>(i), r + 4, 12);
+            for (int k = 0; k < 3; k++) {
+                float v = r[k] / r[3];
+                if (v == v) { lo[k] = v < lo[k] ? v : lo[k]; hi[k] = v > hi[k] ? v : hi[k]; }
+            }
+        }
+        float diag2 = 0;
+        for (int k = 0; k < 3; k++) diag2 += (hi[k] - lo[k]) * (hi[k] - lo[k]);
+        const float radius = diag2 / 10000.f;
+        filterPoints(points, normals, radius);
+        FILE *o = fopen(argv[2], "wb");
         fwrite(&M, 4, 1, o);
         fwrite(tri.data(), 1, (size_t)M * 28, o);
+        int32_t K = points.rows;
+        fwrite(&K, 4, 1, o);
+        fwrite(&radius, 4, 1, o);
+        fwrite(points.data(), 1, (size_t)K * 16, o);
+        fwrite(normals.data(), 1, (size_t)K * 12, o);
         fclose(o);
-        printf("host mirror: %d points\n", M);
+        printf("host mirror: %d points, %d after filterPoints\n", M, K);
     } catch (const mr::Error &e) {
         fprintf(stderr, "mr::Error %d: %s\n", e.code, e.what());
         return 3;

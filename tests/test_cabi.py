@@ -98,7 +98,12 @@ def test_cpp_host_mirror_matches_oracle(tmp_path):
     assert p.returncode == 0, p.stderr
     raw = np.fromfile(tmp_path / "out.bin", np.uint8)
     M = int(raw[:4].view(np.int32)[0])
-    got = raw[4:].view(np.float32).reshape(M, 7)
+    got = raw[4:4 + M * 28].view(np.float32).reshape(M, 7)
+    rest = raw[4 + M * 28:]
+    K = int(rest[:4].view(np.int32)[0])
+    radius = float(rest[4:8].view(np.float32)[0])
+    fp = rest[8:8 + K * 16].view(np.float32).reshape(K, 4)
+    fn = rest[8 + K * 16:8 + K * 28].view(np.float32).reshape(K, 3)
     ro = RenderOracle(160, 120)
     ro.loadMesh(sc.vertices, sc.faces)
     ref = process_main_frame(ro, frames, sc.cameras, 1, [0, 2])
@@ -107,6 +112,12 @@ def test_cpp_host_mirror_matches_oracle(tmp_path):
     assert np.array_equal(ok, ~np.isnan(got).any(1))
     err = np.abs(got[ok, :3] / got[ok, 3:4] - ref[ok, :3] / ref[ok, 3:4]).max()
     assert err <= 1e-4 * sc.scale
+    assert np.array_equal(got, ref, equal_nan=True)
+    # hint.filterPoints(points, normals) through the C++ mirror == the filter oracle on the same cloud
+    from oracle import filter as ofilter
+    keep = ofilter.filter_points(ref[:, :4], radius)["keep"]
+    assert 0 < K < M and K == len(keep)
+    assert np.array_equal(fp, ref[keep, :4], equal_nan=True) and np.array_equal(fn, ref[keep, 4:7], equal_nan=True)
 
 
 def test_register_jacobi_equals_opencv_jacobi():
