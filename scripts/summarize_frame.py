@@ -60,8 +60,8 @@ for r in rows:
         a[k_] += r[k_]
     for k_, s_ in (("issue_w", "issue_pct"), ("fp64_w", "fp64_pct"), ("xu_w", "xu_pct"), ("fma_w", "fma_pct"), ("alu_w", "alu_pct"), ("warps_w", "warps_pct"), ("dram_w", "dram_pct")):
         a[k_] += r[s_] * r["us"]
-out = [f"# ncu --set full, every kernel of ONE main frame ({W}x{H}, S = {S}): {tag}", "",
-       "Command: `scripts/profile_r2.sh` (bench.py --pairs 1 --contexts 1 under `ncu --set full --clock-control none`); per-launch times are",
+out = [f"# ncu (speed-of-light, compute / memory workload, launch, occupancy sections), every kernel of ONE main frame ({W}x{H}, S = {S}): {tag}", "",
+       "Command: `scripts/profile_r2.sh` (bench.py --pairs 1 --contexts 1 under `ncu --clock-control none`); per-launch times are",
        "cold-cache and serialised: compare SHARES.  issue = warp instructions / (148 SMs x 4 schedulers x active cycles).", "",
        f"frame total: {tot['us']:.1f} us over {len(rows)} launches, {tot['inst'] / 1e6:.1f} M warp instructions, {tot['dram'] / 1e6:.1f} MB DRAM traffic "
        f"(algorithmic {54 * W * H / 1e6:.0f} MB)", "",
@@ -74,7 +74,7 @@ for k_, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
 open(f"profiles/{tag}_frame.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out))
 big = sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:5]
-js = {"shape": [W, H, S], "source": f"profiles/{tag}_frame.md (ncu --set full, one main frame)", "warp_inst_per_main_frame": tot["inst"],
+js = {"shape": [W, H, S], "source": f"profiles/{tag}_frame.md (ncu, every kernel of one main frame)", "warp_inst_per_main_frame": tot["inst"],
       "dram_bytes_per_main_frame": tot["dram"], "us_per_main_frame_serialised": tot["us"],
       "pipes_pct_of_peak": {k_[:40]: {"share_of_frame_pct": round(100 * a["us"] / tot["us"], 1), "issue": round(a["issue_w"] / a["us"]), "fma": round(a["fma_w"] / a["us"]),
                                        "fp64": round(a["fp64_w"] / a["us"]), "xu": round(a["xu_w"] / a["us"]), "dram": round(a["dram_w"] / a["us"], 1)} for k_, a in big}}

@@ -268,7 +268,14 @@ def test_farneback_branch(W, H):
     a = mr.calculateFlow(p, n, useFarneback=True)
     b = flow_o.calculate_flow(p, n, use_farneback=True)
     dd = np.abs(a[..., :2] - b[..., :2]).max(-1)
-    assert np.mean(dd > FLOW_TOL_PX) < 1e-3 and np.median(dd) < 1e-4
+    # reported, not hidden: how many pixels exceed the 0.01 px tolerance on multi-pixel motion, where, and by how much
+    exc = dd > FLOW_TOL_PX
+    m = max(8, W // 40)
+    interior = np.zeros_like(exc)
+    interior[m:-m, m:-m] = True
+    print(f"farneback {W}x{H}, 3.3 px translation: {exc.mean():.2e} of the pixels exceed {FLOW_TOL_PX} px (max {dd.max():.3g} px), "
+          f"{(exc & interior).mean():.2e} outside the {m}-pixel border band; median difference {np.median(dd):.2e} px")
+    assert np.mean(exc) < 1e-3 and np.median(dd) < 1e-4
     assert abs(np.median(a[..., 0]) - 3.3) < 0.2
     # fused main-frame step with the reference's -f switch
     if W <= 640:
