@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--sides", type=int, default=None, choices=[1, 2, 4], help="side cameras per main frame (default: 1 for config 4, 4 for config 5)")
     ap.add_argument("--pairs", type=int, default=None, help="MAIN frames per GPU per step (each with S side frames); default 8 (config 4) / 4 (config 5)")
     ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--no-filter-bench", action="store_true", help="skip the filterPoints measurement (N = 1, after the timed regions)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this rank (and its pinned host buffers) to the CPUs local to its GPU")
     ap.add_argument("--link-probe-s", type=float, default=0.3, help="seconds of the all-ranks D2H probe that measures the host link ceiling (0 = skip)")
     ap.add_argument("--cam-step", type=float, default=0.006)
@@ -571,6 +572,40 @@ def main():
         cpu = {"value": len(prs) * S * N / t / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
                "sample": f"{len(prs)} main frame(s) x {S} side frame(s) of {W}x{H} (of the {args.frames}-frame workload), cv2 {cv2.__version__} x{cores} threads + C restatement (OpenMP)"}
 
+    # ---- the step after the path, outside the timed regions: Heuristic::filterPoints on the rows of ONE main frame,
+    # on the device, against its CPU restatement (bounded: one frame's cloud, radius = 3 pixel spacings) ---------------------
+    filt = None
+    if rank == 0 and world == 1 and args.cpu_pairs > 0 and not args.no_filter_bench:
+        try:
+            from oracle import filter as ofilter
+            k_ = (Wm + K + 1) % nbuf
+            m0 = int(counts_dev[k_][0])
+            rows0 = rows_dev[k_][0, :m0].contiguous()
+            fin = torch.isfinite(rows0).all(1)
+            rows0 = rows0[fin].contiguous()
+            d3 = rows0[:, :3] / rows0[:, 3:4]
+            spacing = float((d3[:, 0].max() - d3[:, 0].min())) / W
+            radius = (3.0 * spacing) ** 2
+            out_rows = torch.empty_like(rows0)
+            mr.filter_rows(rows0, radius, ctx=ctx, out=out_rows)          # first call allocates the tables
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            kept_rows, keep = mr.filter_rows(rows0, radius, ctx=ctx, out=out_rows)
+            torch.cuda.synchronize()
+            t_gpu = time.perf_counter() - t0
+            info = mr.api.filter_info(ctx)
+            host_rows = rows0.cpu().numpy()
+            t0 = time.perf_counter()
+            ref = ofilter.filter_points(host_rows[:, :4], radius)
+            t_cpu = time.perf_counter() - t0
+            filt = {"what": "Heuristic::filterPoints (heuristic.cpp:55-176) on the rows of one main frame, device resident", "points": int(len(rows0)),
+                    "neighbour_pairs": int(info["n_edges"]), "power_iterations": int(info["iters"]), "thinning_rounds": int(info["rounds"]),
+                    "survivors": int(len(keep)), "gpu_ms": 1e3 * t_gpu, "cpu_ms": 1e3 * t_cpu, "cpu_kind": "port (oracle/filter_oracle.cpp, 1 core)",
+                    "survivors_bit_identical_to_cpu": bool(np.array_equal(keep.cpu().numpy(), ref["keep"])),
+                    "d2h_bytes_if_filtered_on_device": int(len(keep)) * 28, "d2h_bytes_unfiltered": int(len(rows0)) * 28}
+        except Exception as e:  # noqa: BLE001
+            filt = {"error": str(e)[:200]}
+
     if rank == 0:
         d2h_step = (N * 28 + 4) * B
         e2e = {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": (1 + S) * N * B, "d2h_bytes_per_step": d2h_step,   # the DMA moves the full row capacity (count unknown on the host without a sync)
@@ -607,6 +642,8 @@ def main():
         }
         if xcheck:
             line["exchange_check"] = xcheck
+        if filt:
+            line["filter_points"] = filt
         if cpu:
             line["cpu_baseline"] = cpu
         try:

@@ -9,6 +9,6 @@ mkdir -p gpurun_out
 ncu --section SpeedOfLight --section ComputeWorkloadAnalysis --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
     --metrics smsp__inst_executed.sum,smsp__cycles_active.avg,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
     --clock-control none -k "$OURS" -s 75 -c 72 -f -o gpurun_out/frame_$TAG \
-    python bench.py --steps 1 --warmup 1 --pairs 1 --contexts 1 --cpu-pairs 0 --link-probe-s 0 > gpurun_out/ncu_frame_$TAG.log 2>&1
+    python bench.py --steps 1 --warmup 1 --pairs 1 --contexts 1 --cpu-pairs 0 --link-probe-s 0 --no-filter-bench > gpurun_out/ncu_frame_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_frame_$TAG.log
 ls -la gpurun_out | tail -4

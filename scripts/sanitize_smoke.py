@@ -26,3 +26,24 @@ for i in range(3):
 r.ctx.wait_copies_until(0)
 r.ctx.synchronize()
 print("submit", cnt.tolist(), r.ctx.graph_launches)
+
+# round 2: filterPoints (grid, segmented sorts, seqsum, thinning rounds), frame ingest, and a translated scene (integer-moment
+# route of the normals kernel; the scenes above sit on the z = 0 plane and take the sample loops)
+from tests.test_oracle_filter import cloud
+p = cloud(6000, seed=3)
+ctx = mr.api.Context(16, 16)
+op, on, keep = mr.filterPoints(p, np.zeros((len(p), 3), np.float32), 0.004, ctx=ctx)
+print("filter", len(keep), mr.api.filter_info(ctx))
+bgr = np.random.default_rng(0).integers(0, 256, (96 * 3, 128 * 3, 3)).astype(np.uint8)
+g = mr.api.ingest_frame(mr.api.Context(128, 96), bgr)
+g1 = mr.api.ingest_frame(mr.api.Context(128 * 3, 96 * 3), bgr)
+print("ingest", g.shape, int(g.sum()), g1.shape)
+W, H = 224, 208
+sc = synth.make_scene(W, H, 3, step=0.15, mesh_err=0.03, mesh_res=6)
+T = np.eye(4); T[:3, 3] = (40.0, 25.0, -30.0)
+verts = (sc.vertices.astype(np.float64) @ T.T).astype(np.float32)
+cams = [(c.astype(np.float64) @ np.linalg.inv(T)).astype(np.float32) for c in sc.cameras]
+fr = sc.frames()
+r = mr.Render(W, H, ctx=mr.api.Context(W, H)); r.loadMesh(verts, sc.faces)
+tri = mr.process_main_frame(r, fr[1], cams[1], [fr[0], fr[2]], [cams[0], cams[2]])
+print("translated", tri.shape, r.ctx.normals_stats())
