@@ -286,6 +286,7 @@ int mr_depth(mr_context *ctx, const float camera[16], float *out_depth)
     return MR_OK;
 }
 
+#define MR_QUERY_MAX_PER_CAMERA 4096
 int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const int32_t *rows, const int32_t *cols, int n_per_camera,
                      float *out)
 {
@@ -302,10 +303,17 @@ int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const
     bool dev_out = mr_is_device_ptr(out);
     float *d_out = dev_out ? out : mr_buf<float>(ctx, "q_out", total);
     if (!vis || !d_rows || !d_cols || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_depth_samples", "alloc");
-    for (int i = 0; i < n_cameras; i++) {      // all shots are enqueued back to back; one read-back at the end
-        RC(k_raster(ctx, to_mat4(cameras + 16 * i), vis));
-        RC(k_depth_samples(ctx, vis, d_rows + (size_t)i * n_per_camera, d_cols + (size_t)i * n_per_camera, n_per_camera,
-                           d_out + (size_t)i * n_per_camera));
+    if (n_per_camera <= MR_QUERY_MAX_PER_CAMERA) {
+        // ray queries: the rasteriser's pixel test on the n query pixels of every viewer, no maps rendered
+        const float *d_cams = (const float *)mr_in(ctx, cameras, (size_t)n_cameras * 16 * sizeof(float), "q_cams");
+        if (!d_cams) return mr_fail(ctx, MR_ENOMEM, "mr_depth_samples", "alloc");
+        RC(k_depth_query(ctx, d_cams, n_cameras, d_rows, d_cols, n_per_camera, d_out));
+    } else {
+        for (int i = 0; i < n_cameras; i++) {      // many queries per viewer: render each map, index it on the device
+            RC(k_raster(ctx, to_mat4(cameras + 16 * i), vis));
+            RC(k_depth_samples(ctx, vis, d_rows + (size_t)i * n_per_camera, d_cols + (size_t)i * n_per_camera, n_per_camera,
+                               d_out + (size_t)i * n_per_camera));
+        }
     }
     if (!dev_out) {
         RC(mr_out(ctx, out, d_out, total * sizeof(float)));

@@ -183,6 +183,7 @@ int k_shade(mr_context *ctx, const unsigned long long *d_vis_main, const Mat4 &P
             const uint8_t *d_side_frame, const float *d_shadow_td, uint8_t *d_rgb /*or null*/,
             const uint8_t *d_main_frame /*or null*/, float *d_depth_inout /*or null*/, uint8_t *d_mixed /*or null*/);
 int k_depth_samples(mr_context *ctx, const unsigned long long *d_vis, const int32_t *d_rows, const int32_t *d_cols, int n, float *d_out);
+int k_depth_query(mr_context *ctx, const float *d_cams, int n_cameras, const int32_t *d_rows, const int32_t *d_cols, int n, float *d_out);
 int k_mix_background(mr_context *ctx, const uint8_t *d_rgb, const uint8_t *d_bg, float *d_depth, uint8_t *d_out);
 // flow.cu
 int k_variational_refinement(mr_context *ctx, const uint8_t *d_i0, const uint8_t *d_i1, float *d_flow4);

@@ -11,16 +11,19 @@
 // is order-independent and identical to the sequential oracle (orc_raster).
 // Edge functions are homogeneous (no clipping needed for triangles crossing the camera
 // plane) and exactly negation-symmetric for shared edges => watertight.
+#include <algorithm>
+
 #include "common.cuh"
 
 #define BG_KEY 0xFFFFFFFFFFFFFFFFull
-#define RASTER_CHUNKS 8
 
-struct TriSetup {
+struct alignas(16) TriSetup {
     float e[3][3];
     float zA, zB, zC;
     int valid, x0, x1, y0, y1;
+    int pad[3];            // 80 bytes: whole-struct 128-bit loads
 };
+static_assert(sizeof(TriSetup) == 80, "TriSetup layout");
 
 __device__ __forceinline__ void clip_vertex(const float *P, const float *v, float *c)
 {
@@ -72,11 +75,83 @@ int k_load_mesh(mr_context *ctx, const float *d_vtx, int V, const int32_t *d_fac
 }
 
 // ---- triangle setup -------------------------------------------------------------------
-__global__ void tri_setup_kernel(const float *__restrict__ soup, int F, Mat4 P, int W, int H, TriSetup *__restrict__ out)
+// The pixel tests below (edge_inside x 3, z range) are what DEFINES coverage; the bounding box only has to contain every
+// accepted pixel.  Triangles with all w > 0 get the box of their projected corners (+ 2 pixels), like the oracle.  A
+// triangle that touches or crosses the camera plane has no such box; the oracle walks the whole image for it.  Here
+// its box is that of the convex region  { l0, l1, l2 >= -eps, -1 - eps <= z <= 1 + eps }  intersected with the image
+// rectangle (Sutherland-Hodgman in double on the five affine functions the pixel test itself evaluates, each relaxed by
+// 16 x the worst-case rounding error of its float evaluation, + 2 pixels): a superset of the accepted pixels, so the
+// result is unchanged, but a Render::depth from a viewer sitting ON the mesh (faceCamera, heuristic.cpp:193-247) no longer
+// costs W x H tests per face.
+struct HalfPlane {
+    double a, b, c;        // a X + b Y + c >= 0 (already relaxed)
+};
+
+__device__ __forceinline__ HalfPlane relaxed_plane(float a, float b, float c, float shift, float sign)
 {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const float *tri9 = soup + 9 * f;
+    HalfPlane h;
+    h.a = (double)sign * (double)a;
+    h.b = (double)sign * (double)b;
+    h.c = (double)sign * (double)c + (double)shift;
+    h.c += ((double)fabsf(a) + (double)fabsf(b) + (double)fabsf(c) + 1.0) * (1.0 / 1048576.0) + 1e-30;
+    return h;
+}
+
+// clips the polygon (px, py, n) by h; returns the new vertex count (<= n + 1)
+__device__ int clip_poly(double *px, double *py, int n, const HalfPlane &h)
+{
+    double qx[12], qy[12];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const int j = i + 1 == n ? 0 : i + 1;
+        const double di = h.a * px[i] + h.b * py[i] + h.c, dj = h.a * px[j] + h.b * py[j] + h.c;
+        if (di >= 0.0) { qx[m] = px[i]; qy[m] = py[i]; m++; }
+        if ((di >= 0.0) != (dj >= 0.0)) {
+            const double t = di / (di - dj);
+            qx[m] = px[i] + (px[j] - px[i]) * t;
+            qy[m] = py[i] + (py[j] - py[i]) * t;
+            m++;
+        }
+    }
+    for (int i = 0; i < m; i++) { px[i] = qx[i]; py[i] = qy[i]; }
+    return m;
+}
+
+__device__ void tighten_bbox(TriSetup &t, int W, int H)
+{
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) amax = fmaxf(amax, fabsf(t.e[i][k]));
+    amax = fmaxf(amax, fmaxf(fabsf(t.zA), fmaxf(fabsf(t.zB), fabsf(t.zC))));
+    if (!(amax < 1e30f)) return;                       // NaN / inf / huge coefficients: keep the whole image
+    double px[12] = {-1.0, 1.0, 1.0, -1.0}, py[12] = {-1.0, -1.0, 1.0, 1.0};
+    int n = 4;
+#pragma unroll 1
+    for (int k = 0; k < 5 && n > 0; k++) {
+        HalfPlane h;
+        if (k < 3) h = relaxed_plane(t.e[k][0], t.e[k][1], t.e[k][2], 0.f, 1.f);
+        else if (k == 3) h = relaxed_plane(t.zA, t.zB, t.zC, 1.f, 1.f);        // z >= -1
+        else h = relaxed_plane(t.zA, t.zB, t.zC, 1.f, -1.f);                   // z <= 1
+        n = clip_poly(px, py, n, h);
+    }
+    if (n == 0) { t.x0 = 0; t.x1 = -1; t.y0 = 0; t.y1 = -1; return; }
+    double xmin = 2.0, xmax = -2.0, ymin = 2.0, ymax = -2.0;
+    for (int i = 0; i < n; i++) {
+        xmin = fmin(xmin, px[i]); xmax = fmax(xmax, px[i]);
+        ymin = fmin(ymin, py[i]); ymax = fmax(ymax, py[i]);
+    }
+    if (!(xmin >= -1.5 && xmax <= 1.5 && ymin >= -1.5 && ymax <= 1.5)) return;
+    // pixel centre of column c is X = (c + 0.5) * 2 / W - 1, of row r  Y = 1 - (r + 0.5) * 2 / H
+    const double c0 = (xmin + 1.0) * 0.5 * W - 0.5 - 2.0, c1 = (xmax + 1.0) * 0.5 * W - 0.5 + 2.0;
+    const double r0 = (1.0 - ymax) * 0.5 * H - 0.5 - 2.0, r1 = (1.0 - ymin) * 0.5 * H - 0.5 + 2.0;
+    t.x0 = max(0, (int)floor(c0)); t.x1 = min(W - 1, (int)ceil(c1));
+    t.y0 = max(0, (int)floor(r0)); t.y1 = min(H - 1, (int)ceil(r1));
+}
+
+__device__ __forceinline__ void compute_setup(const float *__restrict__ tri9, const Mat4 &P, int W, int H, TriSetup &t)
+{
     float c[3][4];
 #pragma unroll
     for (int i = 0; i < 3; i++) clip_vertex(P.m, tri9 + 3 * i, c[i]);
@@ -89,7 +164,6 @@ __global__ void tri_setup_kernel(const float *__restrict__ soup, int F, Mat4 P, 
         e[i][2] = a[0] * b[1] - b[0] * a[1];
     }
     float det = (c[0][0] * e[0][0] + c[0][1] * e[0][1]) + c[0][3] * e[0][2];
-    TriSetup t;
     t.valid = 0;
     t.x0 = 0; t.x1 = -1; t.y0 = 0; t.y1 = -1;
     t.zA = t.zB = t.zC = 0.f;
@@ -109,6 +183,7 @@ __global__ void tri_setup_kernel(const float *__restrict__ soup, int F, Mat4 P, 
         t.zC = ((t.e[0][2] * c[0][2] + t.e[1][2] * c[1][2]) + t.e[2][2] * c[2][2]) / adet;
         t.valid = 1;
         t.x0 = 0; t.x1 = W - 1; t.y0 = 0; t.y1 = H - 1;
+        bool boxed = false;
         if (c[0][3] > 0.f && c[1][3] > 0.f && c[2][3] > 0.f) {
             float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
             bool bad = false;
@@ -125,10 +200,36 @@ __global__ void tri_setup_kernel(const float *__restrict__ soup, int F, Mat4 P, 
                 if (fx1 < (float)(W - 1)) t.x1 = fx1 > -1.f ? (int)fx1 : -1;
                 if (fy0 > 0.f) t.y0 = fy0 < (float)H ? (int)fy0 : H;
                 if (fy1 < (float)(H - 1)) t.y1 = fy1 > -1.f ? (int)fy1 : -1;
+                boxed = true;
             }
         }
+        if (!boxed) tighten_bbox(t, W, H);
     }
+}
+
+// Work split by box size: up to RASTER_SMALL_MAX pixels -> ONE WARP of raster_small_kernel walks the box; above that the
+// triangle is appended to the medium or the large list, whose (triangle, row band) items the persistent warps of
+// raster_big_kernel consume (16 bands for a medium triangle, walked like a small box; 64 for a large one, one row at a time, columns restricted
+// to the row's span of the relaxed half-planes).
+#define RASTER_SMALL_MAX 1024
+#define RASTER_MEDIUM_MAX 65536
+#define RASTER_BANDS_MEDIUM 16
+#define RASTER_BANDS_LARGE 64
+
+// lists: cnt[0] = medium count, cnt[1] = large count; medium indices at list[0 .. F), large ones at list[F .. 2F)
+__global__ void tri_setup_kernel(const float *__restrict__ soup, int F, Mat4 P, int W, int H, TriSetup *__restrict__ out,
+                                 int *__restrict__ list, int *__restrict__ cnt, int direct)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    TriSetup t;
+    compute_setup(soup + 9 * (size_t)f, P, W, H, t);
     out[f] = t;
+    const long long area = (long long)max(0, t.x1 - t.x0 + 1) * (long long)max(0, t.y1 - t.y0 + 1);
+    if (!direct && t.valid && area > RASTER_SMALL_MAX) {
+        if (area <= RASTER_MEDIUM_MAX) list[atomicAdd(cnt, 1)] = f;
+        else list[F + atomicAdd(cnt + 1, 1)] = f;
+    }
 }
 
 __device__ __forceinline__ bool edge_inside(const float *e, float X, float Y)
@@ -140,32 +241,175 @@ __device__ __forceinline__ bool edge_inside(const float *e, float X, float Y)
     return e[0] > 0.f || (e[0] == 0.f && e[1] > 0.f);
 }
 
-// grid = (F, RASTER_CHUNKS): each block walks a horizontal band of one triangle's bounding box.
-__global__ void __launch_bounds__(128) raster_kernel(const TriSetup *__restrict__ setups, int W, int H,
-                                                     unsigned long long *__restrict__ vis)
+// the pixel test of the oracle's orc_raster: true + z if triangle t covers the centre of pixel (row, col)
+__device__ __forceinline__ bool pixel_test(const TriSetup &t, int row, int col, float sx, float sy, float *z_out)
+{
+    float X = ((float)col + 0.5f) * sx - 1.0f;
+    float Y = 1.0f - ((float)row + 0.5f) * sy;
+    if (!edge_inside(t.e[0], X, Y) || !edge_inside(t.e[1], X, Y) || !edge_inside(t.e[2], X, Y)) return false;
+    float z = ((t.zA * X + t.zB * Y) + t.zC) + 0.0f;
+    if (!(z >= -1.0f && z < 1.0f)) return false;
+    *z_out = z;
+    return true;
+}
+
+__device__ __forceinline__ void load_setup_warp(const TriSetup *__restrict__ src, TriSetup &t)
+{
+    // every lane reads the same 80 bytes: broadcast loads served by one L1 line pair
+    const int4 *p = reinterpret_cast<const int4 *>(src);
+    int4 *q = reinterpret_cast<int4 *>(&t);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(TriSetup) / 16); i++) q[i] = __ldg(p + i);
+}
+
+// i -> (i / bw, i % bw) for 0 <= i < 2^17, 1 <= bw < 2^13 without the integer-division sequence: float reciprocal + fix-up
+__device__ __forceinline__ void divmod_small(int i, int bw, float inv_bw, int *q, int *r)
+{
+    int qq = __float2int_rz(((float)i + 0.5f) * inv_bw);
+    int rr = i - qq * bw;
+    if (rr < 0) { qq--; rr += bw; }
+    else if (rr >= bw) { qq++; rr -= bw; }
+    *q = qq; *r = rr;
+}
+
+// one warp walks `rows` rows of the triangle's box from row r0 on
+__device__ __forceinline__ void walk_box(const TriSetup &t, int f, int r0, int rows, int lane, int W, float sx, float sy,
+                                         unsigned long long *__restrict__ vis)
+{
+    const int bw = t.x1 - t.x0 + 1, total = bw * rows;
+    const float inv_bw = 1.0f / (float)bw;
+    for (int i = lane; i < total; i += 32) {
+        int dr, dc;
+        divmod_small(i, bw, inv_bw, &dr, &dc);
+        const int row = r0 + dr, col = t.x0 + dc;
+        float z;
+        if (!pixel_test(t, row, col, sx, sy, &z)) continue;
+        atomicMin(&vis[(size_t)row * W + col], ((unsigned long long)z_to_ord(z) << 32) | (unsigned int)f);
+    }
+}
+
+// small boxes: one warp per triangle (its own kernel: 34 registers, so that a 10^6-face mesh runs at full occupancy)
+__global__ void __launch_bounds__(256) raster_small_kernel(const TriSetup *__restrict__ setups, int F, int W, int H,
+                                                           unsigned long long *__restrict__ vis)
+{
+    const int lane = threadIdx.x & 31;
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= F) return;
+    TriSetup t;
+    load_setup_warp(setups + f, t);
+    if (!t.valid) return;
+    const int bw = t.x1 - t.x0 + 1, bh = t.y1 - t.y0 + 1;
+    if (bw <= 0 || bh <= 0 || (long long)bw * bh > RASTER_SMALL_MAX) return;
+    walk_box(t, f, t.y0, bh, lane, W, 2.0f / (float)W, 2.0f / (float)H, vis);
+}
+
+// Rows r0, r0 + step, ... < r1 of a LARGE box, one warp: per row only the columns that can pass the five relaxed half-planes
+//   a X + (b Y + c) >= 0   <=>   X >= -(b Y + c) / a  (a > 0)   or   X <= -(b Y + c) / a  (a < 0)
+// -- a superset of the accepted pixels (+ 2 columns for the rounding of the reciprocal and of the pixel centre).
+__device__ __forceinline__ void walk_spans(const TriSetup &t, int f, int r0, int r1, int step, int lane, int W, float sx, float sy,
+                                           unsigned long long *__restrict__ vis)
+{
+    double hb[5], hc[5], hinv[5];          // hinv = -1 / a, 0 when a == 0
+    int hsgn[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        HalfPlane h;
+        if (k < 3) h = relaxed_plane(t.e[k][0], t.e[k][1], t.e[k][2], 0.f, 1.f);
+        else if (k == 3) h = relaxed_plane(t.zA, t.zB, t.zC, 1.f, 1.f);
+        else h = relaxed_plane(t.zA, t.zB, t.zC, 1.f, -1.f);
+        hb[k] = h.b; hc[k] = h.c;
+        hsgn[k] = h.a > 0.0 ? 1 : (h.a < 0.0 ? -1 : 0);
+        hinv[k] = hsgn[k] ? -1.0 / h.a : 0.0;
+    }
+    for (int row = r0; row < r1; row += step) {
+        const double Y = (double)(1.0f - ((float)row + 0.5f) * sy);
+        double lo = -2.0, hi = 2.0;
+        bool empty = false;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const double r = hb[k] * Y + hc[k];
+            const double x = r * hinv[k];
+            if (hsgn[k] > 0) lo = fmax(lo, x);
+            else if (hsgn[k] < 0) hi = fmin(hi, x);
+            else if (r < 0.0) empty = true;         // (NaN coefficients fall through: whole box)
+        }
+        if (empty || lo > hi + 1e-6) continue;
+        int c_lo = t.x0, c_hi = t.x1;
+        if (lo > -1.5) c_lo = max(c_lo, (int)floor((lo + 1.0) * 0.5 * W - 0.5) - 2);
+        if (hi < 1.5) c_hi = min(c_hi, (int)ceil((hi + 1.0) * 0.5 * W - 0.5) + 2);
+        for (int col = c_lo + lane; col <= c_hi; col += 32) {
+            float z;
+            if (!pixel_test(t, row, col, sx, sy, &z)) continue;
+            atomicMin(&vis[(size_t)row * W + col], ((unsigned long long)z_to_ord(z) << 32) | (unsigned int)f);
+        }
+    }
+}
+
+// Few triangles (F <= RASTER_DIRECT_MAX_F, e.g. the alpha-shape proxy of the first outer iteration): small AND medium boxes
+// are walked by a (F, 8) grid of 128-thread CTAs, one row band each -- thousands of CTAs of a few pixels per thread hide
+// the latency that a warp-per-item walk of so few items cannot; a large box is walked by the same CTAs row by row with spans.
+// No lists, no second launch.
+#define RASTER_DIRECT_MAX_F 4096
+#define RASTER_DIRECT_BANDS 8
+__global__ void __launch_bounds__(128) raster_direct_kernel(const TriSetup *__restrict__ setups, int W, int H, unsigned long long *__restrict__ vis)
 {
     __shared__ TriSetup t;
-    int f = blockIdx.x;
+    const int f = blockIdx.x;
     if (threadIdx.x < sizeof(TriSetup) / 4) ((int *)&t)[threadIdx.x] = ((const int *)&setups[f])[threadIdx.x];
     __syncthreads();
     if (!t.valid) return;
-    int bw = t.x1 - t.x0 + 1, bh = t.y1 - t.y0 + 1;
+    const int bw = t.x1 - t.x0 + 1, bh = t.y1 - t.y0 + 1;
     if (bw <= 0 || bh <= 0) return;
-    int rows_per = (bh + gridDim.y - 1) / gridDim.y;
-    int r0 = t.y0 + blockIdx.y * rows_per;
-    int r1 = min(r0 + rows_per, t.y1 + 1);
+    const int rows_per = (bh + gridDim.y - 1) / gridDim.y;
+    const int r0 = t.y0 + blockIdx.y * rows_per, r1 = min(r0 + rows_per, t.y1 + 1);
     if (r0 >= r1) return;
-    float sx = 2.0f / (float)W, sy = 2.0f / (float)H;
-    int total = bw * (r1 - r0);
+    const float sx = 2.0f / (float)W, sy = 2.0f / (float)H;
+    if ((long long)bw * bh > RASTER_MEDIUM_MAX) {
+        walk_spans(t, f, r0 + (threadIdx.x >> 5), r1, blockDim.x >> 5, threadIdx.x & 31, W, sx, sy, vis);
+        return;
+    }
+    const int total = bw * (r1 - r0);
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        int row = r0 + i / bw, col = t.x0 + i % bw;
-        float X = ((float)col + 0.5f) * sx - 1.0f;
-        float Y = 1.0f - ((float)row + 0.5f) * sy;
-        if (!edge_inside(t.e[0], X, Y) || !edge_inside(t.e[1], X, Y) || !edge_inside(t.e[2], X, Y)) continue;
-        float z = ((t.zA * X + t.zB * Y) + t.zC) + 0.0f;
-        if (!(z >= -1.0f && z < 1.0f)) continue;
-        unsigned long long key = ((unsigned long long)z_to_ord(z) << 32) | (unsigned int)f;
-        atomicMin(&vis[(size_t)row * W + col], key);
+        const int row = r0 + i / bw, col = t.x0 + i % bw;
+        float z;
+        if (!pixel_test(t, row, col, sx, sy, &z)) continue;
+        atomicMin(&vis[(size_t)row * W + col], ((unsigned long long)z_to_ord(z) << 32) | (unsigned int)f);
+    }
+}
+
+// One (triangle, row band) item per warp.  Per row the columns that can pass the five relaxed half-planes
+//   a X + (b Y + c) >= 0   <=>   X >= -(b Y + c) / a  (a > 0)   or   X <= -(b Y + c) / a  (a < 0)
+// are a superset of the accepted pixels (+ 2 columns for the rounding of the reciprocal and of the pixel centre).
+// cnt[0], cnt[1]: list lengths (written by tri_setup_kernel), cnt[2]: CTAs that have finished; the last one to finish
+// zeroes all three for the next call, so no memset has to precede tri_setup_kernel.
+__global__ void __launch_bounds__(256) raster_big_kernel(const TriSetup *__restrict__ setups, int F, const int *__restrict__ list,
+                                                         int *__restrict__ cnt, int W, int H, unsigned long long *__restrict__ vis)
+{
+    const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int bid = blockIdx.x, nbig = gridDim.x;
+    const long long warp0 = (long long)bid * nwarp + (threadIdx.x >> 5), nwarps = (long long)nbig * nwarp;
+    const long long n_med = (long long)cnt[0] * RASTER_BANDS_MEDIUM, items = n_med + (long long)cnt[1] * RASTER_BANDS_LARGE;
+    const float sx = 2.0f / (float)W, sy = 2.0f / (float)H;
+    __syncthreads();                                   // every thread has read the counts
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(cnt + 2, 1) == nbig - 1) { cnt[0] = 0; cnt[1] = 0; cnt[2] = 0; }
+    }
+    for (long long it = warp0; it < items; it += nwarps) {
+        int f, band, nb;
+        if (it < n_med) { f = list[it / RASTER_BANDS_MEDIUM]; band = (int)(it % RASTER_BANDS_MEDIUM); nb = RASTER_BANDS_MEDIUM; }
+        else { const long long j = it - n_med; f = list[F + j / RASTER_BANDS_LARGE]; band = (int)(j % RASTER_BANDS_LARGE); nb = RASTER_BANDS_LARGE; }
+        TriSetup t;
+        load_setup_warp(setups + f, t);
+        const int bh = t.y1 - t.y0 + 1;
+        const int rows_per = (bh + nb - 1) / nb;
+        const int r0 = t.y0 + band * rows_per, r1 = min(r0 + rows_per, t.y1 + 1);
+        if (r0 >= r1) continue;
+        if (nb == RASTER_BANDS_MEDIUM) {
+            walk_box(t, f, r0, r1 - r0, lane, W, sx, sy, vis);      // medium box: plain walk of the band
+            continue;
+        }
+        walk_spans(t, f, r0, r1, 1, lane, W, sx, sy, vis);
     }
 }
 
@@ -173,13 +417,26 @@ int k_raster(mr_context *ctx, const Mat4 &P, unsigned long long *d_vis)
 {
     MR_CUDA(ctx, cudaMemsetAsync(d_vis, 0xFF, ctx->N * sizeof(unsigned long long), ctx->stream));
     if (ctx->F == 0) return MR_OK;
+    const int F = ctx->F;
     float *soup = mr_buf<float>(ctx, "soup", 0);
     TriSetup *setups = mr_buf<TriSetup>(ctx, "setup", 0);
-    tri_setup_kernel<<<cdiv(ctx->F, 128), 128, 0, ctx->stream>>>(soup, ctx->F, P, ctx->W, ctx->H, setups);
+    const bool fresh = !ctx->bufs.count("raster_lists") || ctx->bufs["raster_lists"].bytes < (2 * (size_t)F + 4) * sizeof(int);
+    int *big = mr_buf<int>(ctx, "raster_lists", 2 * (size_t)F + 4);      // [0..2]: counters (self-resetting), [4..]: the two lists
+    if (!big) return mr_fail(ctx, MR_ENOMEM, "raster_lists", "alloc");
+    if (fresh) MR_CUDA(ctx, cudaMemsetAsync(big, 0, 4 * sizeof(int), ctx->stream));
+    const bool direct = F <= RASTER_DIRECT_MAX_F;
+    tri_setup_kernel<<<cdiv(F, 128), 128, 0, ctx->stream>>>(soup, F, P, ctx->W, ctx->H, setups, big + 4, big, direct ? 1 : 0);
     MR_LAUNCH_CHECK(ctx, "tri_setup_kernel");
-    dim3 grid(ctx->F, RASTER_CHUNKS);
-    raster_kernel<<<grid, 128, 0, ctx->stream>>>(setups, ctx->W, ctx->H, d_vis);
-    MR_LAUNCH_CHECK(ctx, "raster_kernel");
+    if (direct) {
+        raster_direct_kernel<<<dim3(F, RASTER_DIRECT_BANDS), 128, 0, ctx->stream>>>(setups, ctx->W, ctx->H, d_vis);
+        MR_LAUNCH_CHECK(ctx, "raster_direct_kernel");
+        return MR_OK;
+    }
+    raster_small_kernel<<<cdiv(F, 8), 256, 0, ctx->stream>>>(setups, F, ctx->W, ctx->H, d_vis);
+    MR_LAUNCH_CHECK(ctx, "raster_small_kernel");
+    const int ctas = (int)std::min<long long>(((long long)F * RASTER_BANDS_LARGE + 7) / 8, 148 * 16);
+    raster_big_kernel<<<ctas, 256, 0, ctx->stream>>>(setups, F, big + 4, big, ctx->W, ctx->H, d_vis);
+    MR_LAUNCH_CHECK(ctx, "raster_big_kernel");
     return MR_OK;
 }
 
@@ -430,6 +687,84 @@ __global__ void depth_samples_kernel(const unsigned long long *__restrict__ vis,
         if (k != BG_KEY) d = ord_to_z((unsigned int)(k >> 32));
     }
     out[i] = d;
+}
+
+// The same queries WITHOUT rendering the maps ("200 depth() renders -> 200 single-pixel ray queries"):
+// one thread per (viewer, triangle) builds the triangle's setup for that viewer and runs the rasteriser's own pixel test
+// on the viewer's n query pixels only; the nearest hit per query is an atomicMin on the same 64-bit key.  Same setup,
+// same pixel test, same tie rule as k_raster, so the answers are bit-identical to indexing the full maps
+// (tests/test_gpu_edge_and_fullsize.py), at F x n tests per viewer instead of a W x H raster.
+#define QUERY_CHUNK 256
+__global__ void __launch_bounds__(128) depth_query_kernel(const float *__restrict__ soup, int F, const float *__restrict__ cams, int W, int H,
+                                                          const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, int n,
+                                                          unsigned long long *__restrict__ keys)
+{
+    __shared__ Mat4 P;
+    __shared__ int2 q[QUERY_CHUNK];
+    const int cam = blockIdx.y;
+    if (threadIdx.x < 16) P.m[threadIdx.x] = cams[16 * (size_t)cam + threadIdx.x];
+    __syncthreads();
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    TriSetup t;
+    t.valid = 0;
+    if (f < F) compute_setup(soup + 9 * (size_t)f, P, W, H, t);
+    const float sx = 2.0f / (float)W, sy = 2.0f / (float)H;
+    const long long last = (long long)W * H - 1;
+    for (int base = 0; base < n; base += QUERY_CHUNK) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < QUERY_CHUNK; j += blockDim.x) {
+            int2 v = make_int2(-1, -1);
+            if (base + j < n) {
+                const int r = rows[(size_t)cam * n + base + j], c = cols[(size_t)cam * n + base + j];
+                if (r >= 0 && r < H && c >= 0 && c <= W) {
+                    long long idx = (long long)r * W + c;          // depth.at<float>(row, col) on a continuous Mat
+                    if (idx > last) idx = last;
+                    v = make_int2((int)(idx / W), (int)(idx % W));
+                }
+            }
+            q[j] = v;
+        }
+        __syncthreads();
+        if (!t.valid) continue;
+        const int m = min(QUERY_CHUNK, n - base);
+        for (int j = 0; j < m; j++) {
+            const int2 v = q[j];
+            if (v.x < t.y0 || v.x > t.y1 || v.y < t.x0 || v.y > t.x1) continue;
+            float z;
+            if (!pixel_test(t, v.x, v.y, sx, sy, &z)) continue;
+            atomicMin(&keys[(size_t)cam * n + base + j], ((unsigned long long)z_to_ord(z) << 32) | (unsigned int)f);
+        }
+    }
+}
+
+__global__ void resolve_query_kernel(const unsigned long long *__restrict__ keys, size_t total, float *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    unsigned long long k = keys[i];
+    out[i] = (k == BG_KEY) ? MR_BACKGROUND_DEPTH : ord_to_z((unsigned int)(k >> 32));
+}
+
+int k_depth_query(mr_context *ctx, const float *d_cams, int n_cameras, const int32_t *d_rows, const int32_t *d_cols, int n, float *d_out)
+{
+    const size_t total = (size_t)n_cameras * n;
+    if (total == 0) return MR_OK;
+    unsigned long long *keys = mr_buf<unsigned long long>(ctx, "q_keys", total);
+    if (!keys) return mr_fail(ctx, MR_ENOMEM, "q_keys", "alloc");
+    MR_CUDA(ctx, cudaMemsetAsync(keys, 0xFF, total * sizeof(unsigned long long), ctx->stream));
+    if (ctx->F > 0) {
+        float *soup = mr_buf<float>(ctx, "soup", 0);
+        for (int c0 = 0; c0 < n_cameras; c0 += 32768) {            // gridDim.y limit
+            const int nc = std::min(32768, n_cameras - c0);
+            dim3 grid(cdiv(ctx->F, 128), nc);
+            depth_query_kernel<<<grid, 128, 0, ctx->stream>>>(soup, ctx->F, d_cams + 16 * (size_t)c0, ctx->W, ctx->H, d_rows + (size_t)c0 * n,
+                                                              d_cols + (size_t)c0 * n, n, keys + (size_t)c0 * n);
+            MR_LAUNCH_CHECK(ctx, "depth_query_kernel");
+        }
+    }
+    resolve_query_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, total, d_out);
+    MR_LAUNCH_CHECK(ctx, "resolve_query_kernel");
+    return MR_OK;
 }
 
 int k_depth_samples(mr_context *ctx, const unsigned long long *d_vis, const int32_t *d_rows, const int32_t *d_cols, int n, float *d_out)

@@ -185,6 +185,7 @@ def test_depth_samples_match_full_depth_maps():
     cols = rng.integers(-3, W + 3, (m, n)).astype(np.int32)
     cols[0, :5] = W                                    # the reference's off-by-one column
     rows[0, :5] = [0, 5, H - 2, H - 1, 7]
+    r.depthSamples(sc.cameras[:m], rows, cols)         # first call: allocations, lazy module load
     t0 = time.perf_counter()
     got = r.depthSamples(sc.cameras[:m], rows, cols)
     t_batched = time.perf_counter() - t0
