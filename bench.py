@@ -205,9 +205,11 @@ def main():
     ap.add_argument("--vr-impl", type=int, default=None)
     ap.add_argument("--contexts", type=int, default=3, help="library contexts (streams) per GPU; main frames alternate between them so that "
                     "one pair's kernel tails / low-occupancy phases overlap the other's (measured +15 %% at 2)")
-    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
-                    help="N > 1: how the point rows reach every rank -- p2p: copy-engine pushes into the peers' buffers over NVLink "
-                         "(CUDA IPC, no SMs); nccl: all_gather_into_tensor")
+    ap.add_argument("--exchange", choices=["auto", "mcast", "p2p", "nccl"], default="auto",
+                    help="N > 1: how the point rows reach every rank -- mcast: ONE push per rank to an NVSwitch multicast address (a few CTAs "
+                         "of multimem.st; lands in every rank's buffer); p2p: one copy-engine push per peer over NVLink (CUDA IPC), "
+                         "no SMs; nccl: all_gather_into_tensor; auto = p2p (measured at 8 GPUs: 13.2 ms per step against 13.4 for mcast -- what "
+                         "slows the step is the 7 x 464 MB ARRIVING at every GPU, which multicast does not reduce)")
     ap.add_argument("--xchg-repeat", type=int, default=1,
                     help="debug: push every slot this many times (emulates the per-GPU exchange volume of a larger world on few GPUs)")
     ap.add_argument("--graphs", type=int, default=None, choices=[0, 1, 2],
@@ -274,29 +276,42 @@ def main():
             lib_stream.wait_stream(st)
 
     nbuf = 2 if world > 1 else 1
-    use_p2p = world > 1 and args.exchange == "p2p"
+    use_p2p = world > 1 and args.exchange != "nccl"
+    use_mcast = False
     xch = None
     if use_p2p:
         # kernel-free exchange: per buffer set, every rank owns a receive buffer with one slot per rank (rows of B pairs at
-        # full capacity, then the B counts), mapped into every peer over CUDA IPC; the normals kernel writes this rank's rows
-        # straight into its own slot, which is then DMA'd into the same slot of every peer (mr_xchg_push)
-        from mesh_reconstruction_b200.shard import PeerExchange
+        # full capacity, then the B counts).  p2p: the buffer is mapped into every peer over CUDA IPC, the normals kernel writes
+        # this rank's rows straight into its own slot, which is then DMA'd into the same slot of every peer (mr_xchg_push);
+        # mcast: the buffers are bound to an NVSwitch multicast object and ONE DMA per step reaches all of them
+        from mesh_reconstruction_b200.shard import McastExchange, PeerExchange
         rows_bytes = (B * N * 28 + 255) // 256 * 256
-        xch = []
-        try:
-            for _ in range(nbuf):
-                xch.append(PeerExchange(ctx, rows_bytes + B * 4, dev))      # collective; raises on every rank or on none
-            ok = 1
-        except Exception as e:  # noqa: BLE001  (CUDA IPC / peer access unavailable on this box)
-            print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
-            for x in xch:                    # an exchange that was already built must not stay mapped in the peers
-                x.close()
-            ok = 0
-        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)           # every rank must take the same path
-        if int(okt.item()) == 0:
-            use_p2p, xch = False, None
-    if use_p2p:
+        kinds = {"auto": ["p2p"], "mcast": ["mcast", "p2p"], "p2p": ["p2p"]}[args.exchange]
+        for kind in kinds:
+            xch = []
+            try:
+                for _ in range(nbuf):
+                    xch.append((McastExchange if kind == "mcast" else PeerExchange)(ctx, rows_bytes + B * 4, dev))   # collective; raises on every rank or on none
+                ok = 1
+            except Exception as e:  # noqa: BLE001  (multicast / CUDA IPC / peer access unavailable on this box)
+                print(f"bench.py: rank {rank}: {kind} exchange unavailable ({e})", file=sys.stderr)
+                for x in xch:                    # an exchange that was already built must not stay mapped in the peers
+                    x.close()
+                ok = 0
+            okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)           # every rank must take the same path
+            if int(okt.item()) == 1:
+                use_mcast = kind == "mcast"
+                break
+            xch = None
+        if xch is None:
+            print(f"bench.py: rank {rank}: using the NCCL all-gather", file=sys.stderr)
+            use_p2p = False
+    if use_p2p and use_mcast:
+        rows_dev = [x.out((B, N, 7)) for x in xch]
+        counts_dev = [x.out((B,), torch.int32, offset_bytes=rows_bytes) for x in xch]
+        xflag = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    elif use_p2p:
         rows_dev = [x.slot(rank, (B, N, 7)) for x in xch]
         counts_dev = [x.slot(rank, (B,), torch.int32, offset_bytes=rows_bytes) for x in xch]
         for c_ in counts_dev:
@@ -625,6 +640,7 @@ def main():
                        "contexts_per_gpu": nctx, "flow": "farneback (-f)" if args.farneback else "variational refinement (reference default)", "mesh_faces": int(len(scene.faces)), "points_per_main_frame": m_mean,
                        "l2": f"working set per step ({B} main frames x ~{((16 * 4 + 24) * S + 40) * N / 1e6:.0f} MB of planes) exceeds the 126 MB L2; no explicit flush",
                        "exchange": ("none (single GPU)" if world == 1 else
+                                    "ONE push of rows + counts per rank and step to an NVSwitch multicast address (mr_xchg_push_mcast: a few CTAs of 128-bit multimem.st on a high-priority stream; the switch replicates it into every rank's buffer), overlapped with the next step" if use_mcast else
                                     "copy-engine pushes of rows + counts into every peer's buffer over NVLink (CUDA IPC, mr_xchg_push; no SMs), overlapped with the next step" if use_p2p else
                                     "async nccl all_gather_into_tensor of point rows + counts per step, overlapped with the next step")},
             "e2e": e2e,

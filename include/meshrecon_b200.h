@@ -178,6 +178,12 @@ int mr_xchg_open(mr_context *ctx, const unsigned char ipc_handle[64], void **pee
 int mr_xchg_close(mr_context *ctx, void *peer_ptr);
 int mr_xchg_push(mr_context *ctx, void *peer_dst, const void *src, size_t bytes);
 void *mr_xchg_stream(mr_context *ctx);
+/* The same push through an NVSwitch MULTICAST mapping of the ranks' receive buffers (cuMulticastCreate / cuMulticastBindMem
+ * by the host, e.g. torch.distributed's symmetric memory): one 128-bit multimem.st per 16 bytes, replicated by the switch
+ * into every rank's buffer, so the rows leave the GPU once instead of world - 1 times.  A few CTAs on the high-priority
+ * push stream (MR_MCAST_CTAS, default 32), ordered after mr_stream(ctx); completion as for mr_xchg_push.  bytes and
+ * both pointers must be multiples of 16. */
+int mr_xchg_push_mcast(mr_context *ctx, void *mcast_dst, const void *src, size_t bytes);
 /* ---- frame ingest  configuration.cpp:226-245 -------------------------------------------------------
  * What Configuration does to every decoded frame before the path sees it: cv::resize(frame, Size(width, height),
  * CV_INTER_AREA) when the clip is larger than the render size (the -s scaling factor), then cv::cvtColor(CV_BGR2GRAY).

@@ -75,6 +75,7 @@ def load_library():
     L.mr_xchg_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
     L.mr_xchg_close.argtypes = [vp, vp]
     L.mr_xchg_push.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mr_xchg_push_mcast.argtypes = [vp, vp, vp, C.c_size_t]
     L.mr_xchg_stream.argtypes = [vp]
     L.mr_xchg_stream.restype = vp
     L.mr_graph_launch_count.argtypes = [vp]

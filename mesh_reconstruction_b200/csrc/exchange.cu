@@ -253,3 +253,52 @@ extern "C" int mr_xchg_push(mr_context *ctx, void *dst, const void *src, size_t 
     if (bytes) MR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->push_stream[i]));
     return MR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multicast push (NVSwitch): `mc_dst` is the multicast mapping of the ranks' receive buffers (cuMulticastBindMem; one
+// store to it is replicated by the switch into the same offset of EVERY rank's buffer), so a rank sends its rows ONCE
+// instead of world - 1 times.  The copy engines reach such an address at 330 GB/s on idle GPUs but only ~35 GB/s
+// while the path's kernels run (profiles/mcast_push_r2.txt), so the write is done by a few CTAs of 128-bit multimem.st
+// instead, on the high-priority push streams: they take the first SM slots that come free and leave them within
+// microseconds.  Ordered after everything queued on mr_stream(ctx); completion is signalled like mr_xchg_push's.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mcast_store_kernel(const uint4 *__restrict__ src, uint4 *mc_dst, size_t n16)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;                                   // four 16-byte loads in flight per thread
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n16; i0 += U * stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (i0 + u * stride < n16) v[u] = __ldcs(src + i0 + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (i0 + u * stride < n16)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i0 + u * stride),
+                             "f"(__uint_as_float(v[u].x)), "f"(__uint_as_float(v[u].y)), "f"(__uint_as_float(v[u].z)), "f"(__uint_as_float(v[u].w))
+                             : "memory");
+    }
+    __threadfence_system();
+}
+
+extern "C" int mr_xchg_push_mcast(mr_context *ctx, void *mc_dst, const void *src, size_t bytes)
+{
+    if (!ctx) return MR_EINVAL;
+    if (!mc_dst || !src || (bytes & 15) || ((uintptr_t)mc_dst & 15) || ((uintptr_t)src & 15))
+        return mr_fail(ctx, MR_EINVAL, "mr_xchg_push_mcast", "null or not 16-byte aligned");
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_push_streams(ctx);
+    if (rc) return rc;
+    static const int n_ctas = []() {                         // MR_MCAST_CTAS (tuning knob)
+        const char *e = getenv("MR_MCAST_CTAS");
+        int n = e ? atoi(e) : 32;
+        return n < 1 ? 1 : (n > 1184 ? 1184 : n);
+    }();
+    MR_CUDA(ctx, cudaEventRecord(ctx->ev_push[0], ctx->stream));
+    MR_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream[0], ctx->ev_push[0], 0));
+    if (bytes) {
+        mcast_store_kernel<<<n_ctas, 256, 0, ctx->push_stream[0]>>>((const uint4 *)src, (uint4 *)mc_dst, bytes / 16);
+        MR_LAUNCH_CHECK(ctx, "mcast_store_kernel");
+    }
+    return MR_OK;
+}

@@ -6,6 +6,8 @@ frame is an independent unit, so ranks take CONTIGUOUS blocks of the sorted main
 in rank order, reproduces the reference's row order (recon.cpp:115-116 appends per main frame).
 One process per GPU; NCCL over NVLink for CUDA tensors, gloo for the CPU tests.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -197,3 +199,73 @@ class PeerExchange:
         if self.ptr:
             self.lib.mr_xchg_free(self.ctx.h, C.c_void_p(self.ptr))
             self.ptr = 0
+
+
+class McastExchange:
+    """The same exchange with ONE push per rank and step: every rank's receive buffer is bound to an NVSwitch multicast
+    object, and a copy-engine DMA to the multicast address lands in the same slot of EVERY rank's buffer (the switch
+    replicates the writes), so a GPU sends its rows once instead of world - 1 times (at 8 GPUs the seven
+    unicast pushes of 464 MB per step are what the copy engines cannot sustain next to the path's kernels).
+
+    The symmetric allocation, the exchange of the shareable handles between the processes and the multicast binding are
+    torch.distributed's symmetric memory (plumbing: cuMemCreate / cuMulticastCreate / cuMulticastBindMem under the hood);
+    the DMA itself is ``mr_xchg_push`` on the library's push streams, ordered after the path's kernels, exactly like
+    :class:`PeerExchange`.  The rows are produced into ``send`` (a plain device buffer: a multicast write also lands in the
+    sender's own slot, and source and destination of a DMA must not alias).  Raises on every rank if the fabric offers
+    no multicast."""
+
+    def __init__(self, ctx, slot_bytes, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.ctx, self.lib, self.group = ctx, ctx.lib, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        err, self.buf, self.hdl, self.mc = None, None, None, 0
+        self.chunks = int(os.environ.get("MR_MCAST_CHUNKS", "4"))
+        self.mode = os.environ.get("MR_MCAST_MODE", "sm")        # "sm": multimem.st kernel, "ce": copy engines
+        try:
+            self.buf = symm.empty(self.slot_bytes * self.world, dtype=torch.uint8, device=self.device)
+            self.hdl = symm.rendezvous(self.buf, group=(group or dist.group.WORLD))
+            self.mc = int(self.hdl.multicast_ptr or 0)
+            if not self.mc:
+                err = "no multicast pointer (NVSwitch multicast unsupported on this fabric / driver)"
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("multicast exchange unavailable: " + (err or "failed on another rank"))
+        self.ptr = self.buf.data_ptr()
+        self.send = torch.zeros(self.slot_bytes, dtype=torch.uint8, device=self.device)
+
+    def slot(self, r, shape, dtype=torch.float32, offset_bytes=0):
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        return torch.as_tensor(_DevMem(self.ptr + r * self.slot_bytes + offset_bytes, shape, typestr), device=self.device)
+
+    def out(self, shape, dtype=torch.float32, offset_bytes=0):
+        """View of the send buffer: hand it to the path as its output buffer."""
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        return torch.as_tensor(_DevMem(self.send.data_ptr() + offset_bytes, shape, typestr), device=self.device)
+
+    def push(self, nbytes=None):
+        import ctypes as C
+        nbytes = self.slot_bytes if nbytes is None else int(nbytes)
+        dst, src = self.mc + self.rank * self.slot_bytes, self.send.data_ptr()
+        if self.mode == "sm":
+            # a few CTAs of 128-bit multimem.st on the high-priority push stream (mr_xchg_push_mcast)
+            self.ctx.check(self.lib.mr_xchg_push_mcast(self.ctx.h, C.c_void_p(dst), C.c_void_p(src), (nbytes + 15) // 16 * 16))
+            return
+        # copy engines: one reaches ~100 GB/s into a multicast address, two or more ~330 GB/s on idle GPUs
+        # (scripts/mcast_push_probe.py) -- but only ~35 GB/s while the path's kernels run
+        step = (nbytes // self.chunks + 255) // 256 * 256
+        for o in range(0, nbytes, step):
+            self.ctx.check(self.lib.mr_xchg_push(self.ctx.h, C.c_void_p(dst + o), C.c_void_p(src + o), min(step, nbytes - o)))
+
+    def signal_stream(self):
+        return torch.cuda.ExternalStream(self.lib.mr_xchg_stream(self.ctx.h), device=self.device)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.hdl = self.buf = None
