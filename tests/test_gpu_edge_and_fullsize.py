@@ -127,11 +127,12 @@ def _pixel_of_rows(rows, P, W, H):
     return row, col
 
 
-@pytest.mark.parametrize("W,H,S,with_oracle", [(1920, 1080, 1, True), (3840, 2160, 4, False)])
+@pytest.mark.parametrize("W,H,S,with_oracle", [(1920, 1080, 1, True), (3840, 2160, 4, True)])
 def test_full_size_properties(W, H, S, with_oracle):
     """BASELINE configs 4 (1080p, S=1) and 5 (4K, S=4) at full size.  Properties: determinism; the fused
     call equals the sequence of individual entry points bit for bit; rows come out in row-major pixel
-    order, one per surviving pixel; at 1080p additionally the full oracle comparison."""
+    order, one per surviving pixel; and the full oracle comparison at both sizes (the 4K, S = 4 oracle run takes ~10-30 s of
+    host time): every flow of every side camera and every point row bit for bit."""
     n = S + 1
     sc = synth.make_scene(W, H, 300, step=0.006, mesh_err=0.02)
     fa = 150
@@ -162,10 +163,10 @@ def test_full_size_properties(W, H, S, with_oracle):
     assert not flows[0][..., 3].any() and np.isfinite(flows[0]).all()
     if with_oracle:
         ref, inter = _oracle_main(sc, frames, fa, sides)
-        assert np.array_equal(flows[0][..., :2], inter["flows"][0][..., :2])
-        _assert_rows(a, ref, sc.scale, "1080p vs oracle")
-        fin = np.isfinite(ref[:, :4]).all(1)
-        assert np.array_equal(a[fin, :4], ref[fin, :4])
+        for i in range(S):                                              # (u, v) and the variance of every side camera
+            assert np.array_equal(flows[i], inter["flows"][i]), i
+        _assert_rows(a, ref, sc.scale, f"{W}x{H} S={S} vs oracle")
+        assert np.array_equal(a, ref, equal_nan=True)                   # whole rows (points + normals), bit for bit
 
 
 def test_depth_samples_match_full_depth_maps():
