@@ -194,6 +194,14 @@ int mr_xchg_push_mcast(mr_context *ctx, void *mcast_dst, const void *src, size_t
  * estimateExposure (off by default, configuration.cpp:25) stay on the host.  Asynchronous for device outputs
  * (enqueued on mr_stream); a host input must stay untouched until the stream has drained. */
 int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, uint8_t *out_gray);
+/* The same when Configuration::estimateExposure is on (configuration.cpp:270-426, off by default): its last step
+ * (configuration.cpp:417-425) replaces the gray conversion by  frame = sum_c channel[c] * exposure[c]  in 8-bit cv::Mat
+ * arithmetic (each product rounded and saturated to uchar, the additions saturating, channel order B, G, R).  The
+ * exposure estimate itself -- a 100-iteration alternating least-squares over the ~20 bundle points of every frame
+ * (3-column pseudo-inverses) -- is KB-sized host work and stays with the caller; exposure_bgr are its three weights for
+ * this frame. */
+int mr_ingest_frame_exposure(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, const float exposure_bgr[3],
+                             uint8_t *out_gray);
 /* BGR2GRAY coefficients: 15 (default) = the 15-bit ones of OpenCV >= 3.4.6 / 4.x (3735, 19235, 9798), 14 = the 14-bit
  * ones of OpenCV 3.0 - 3.4.5 (1868, 9617, 4899) -- the reference does not pin its OpenCV version (Makefile:10). */
 int mr_set_gray_shift(mr_context *ctx, int shift);

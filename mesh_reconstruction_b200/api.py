@@ -97,6 +97,7 @@ def load_library():
     L.mr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.mr_normals_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mr_ingest_frame.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.mr_ingest_frame_exposure.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), vp]
     L.mr_set_gray_shift.argtypes = [vp, C.c_int]
     L.mr_filter_points.argtypes = [vp, vp, vp, C.c_size_t, C.c_float, vp, vp, vp, C.POINTER(C.c_size_t)]
     L.mr_filter_rows.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, vp, C.POINTER(C.c_size_t)]
@@ -448,7 +449,7 @@ def filter_info(ctx, want_arrays=False, n=None):
     return {"n_edges": info[0], "iters": info[1], "rounds": info[2]}
 
 
-def ingest_frame(ctx, bgr, out=None):
+def ingest_frame(ctx, bgr, out=None, exposure=None):
     """``mr_ingest_frame``: what configuration.cpp:226-245 does to a decoded frame -- ``cv::resize(INTER_AREA)`` to the
     context's size when the frame is an integer multiple of it, then ``cv::cvtColor(BGR2GRAY)``.  ``bgr``: h x w x 3 uint8
     (NumPy / pinned or CUDA tensor); returns the H x W gray frame (NumPy, or ``out`` -- e.g. a CUDA tensor)."""
@@ -457,5 +458,9 @@ def ingest_frame(ctx, bgr, out=None):
     if out is None:
         out = np.empty((ctx.H, ctx.W), np.uint8)
     po, ko = _ptr(out, np.uint8)
-    ctx.check(ctx.lib.mr_ingest_frame(ctx.h, pb, w, h, po))
+    if exposure is not None:      # estimateExposure's channel weights (B, G, R) of this frame, configuration.cpp:417-425
+        ex = (C.c_float * 3)(*[float(v) for v in exposure])
+        ctx.check(ctx.lib.mr_ingest_frame_exposure(ctx.h, pb, w, h, ex, po))
+    else:
+        ctx.check(ctx.lib.mr_ingest_frame(ctx.h, pb, w, h, po))
     return out

@@ -826,7 +826,7 @@ int mr_debug_jacobi3(const float cov6[6], float evals3[3], float evecs9[9])
 }
 
 // Frame ingest of Configuration::Configuration (configuration.cpp:226-245): BGR frame -> (INTER_AREA shrink) -> gray.
-int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, uint8_t *out_gray)
+static int ingest_impl(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, const float *exposure, uint8_t *out_gray)
 {
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
@@ -839,12 +839,25 @@ int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_
     const bool dev_out = mr_is_device_ptr(out_gray);
     uint8_t *d_out = dev_out ? out_gray : mr_buf<uint8_t>(ctx, "ingest_gray", ctx->N);
     if (!d_in || !d_out) return mr_fail(ctx, MR_ENOMEM, "mr_ingest_frame", "alloc");
-    RC(k_ingest(ctx, d_in, src_width, src_height, d_out));
+    RC(k_ingest(ctx, d_in, src_width, src_height, d_out, exposure));
     if (!dev_out) {
         RC(mr_out(ctx, out_gray, d_out, ctx->N));
         MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return MR_OK;
+}
+
+int mr_ingest_frame(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, uint8_t *out_gray)
+{
+    return ingest_impl(ctx, bgr, src_width, src_height, nullptr, out_gray);
+}
+
+// The same with estimateExposure's per-frame channel weights instead of BGR2GRAY (configuration.cpp:417-425).
+int mr_ingest_frame_exposure(mr_context *ctx, const uint8_t *bgr, int src_width, int src_height, const float exposure_bgr[3], uint8_t *out_gray)
+{
+    CHECK_CTX(ctx);
+    CHECK_ARG(ctx, exposure_bgr, "null exposure");
+    return ingest_impl(ctx, bgr, src_width, src_height, exposure_bgr, out_gray);
 }
 
 int mr_set_gray_shift(mr_context *ctx, int shift)

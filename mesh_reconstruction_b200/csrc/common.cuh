@@ -192,7 +192,7 @@ int k_compare(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, flo
 int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, float *d_flow4);   // farneback.cu
 int mr_flow_init_tables(mr_context *ctx);
 // ingest.cu
-int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray);
+int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray, const float *exposure = nullptr);
 // filter.cu
 int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const float *d_nrm, int nstride, int n, float radius, float *d_out_pts,
                     int opstride, float *d_out_nrm, int onstride, int *d_out_keep, int *h_count, long long *info);

@@ -12,6 +12,10 @@
 //   * BGR2GRAY 8U: (B * BY + G * GY + R * RY + half) >> shift with the 15-bit coefficients (3735, 19235, 9798) of
 //     OpenCV >= 3.4.6 / 4.x (the cv2 binary the oracle is pinned to) or the 14-bit ones (1868, 9617, 4899) of
 //     OpenCV 3.0 - 3.4.5 (mr_set_gray_shift).
+//   * with estimateExposure on (configuration.cpp:417-425) the gray conversion is replaced by the exposure mix
+//         frame = zeros(8UC1);  for c in B, G, R:  frame += channel[c] * exposure[c]
+//     which cv::Mat evaluates as  t_c = saturate_cast<uchar>(rint((float)channel * (float)exposure[c]))  (convertTo with a
+//     float scale, round half to even) followed by SATURATING 8-bit additions, in channel order.
 #include "common.cuh"
 
 namespace {
@@ -22,8 +26,35 @@ __device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r, 
     return (b * 1868u + g * 9617u + r * 4899u + (1u << 13)) >> 14;
 }
 
+struct Expo {
+    float e[3];
+    int on;
+};
+
+__device__ __forceinline__ unsigned expo_of(unsigned b, unsigned g, unsigned r, const Expo &x)
+{
+    const unsigned ch[3] = {b, g, r};
+    unsigned acc = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float v = (float)ch[c] * x.e[c];
+        int t = 0;
+        // saturate_cast<uchar>(cvRound(v)): cvRound of NaN or of |v| >= 2^31 is the integer indefinite INT_MIN -> 0
+        if (!(v < 2147483648.f)) t = 0;
+        else if (v >= 255.5f) t = 255;
+        else if (v > 0.f) t = __float2int_rn(v);
+        acc = min(acc + (unsigned)t, 255u);                // cv::add on CV_8U saturates
+    }
+    return acc;
+}
+
+__device__ __forceinline__ unsigned out_of(unsigned b, unsigned g, unsigned r, int shift, const Expo &x)
+{
+    return x.on ? expo_of(b, g, r, x) : gray_of(b, g, r, shift);
+}
+
 // factor 1: four pixels per thread (12 bytes in as three 32-bit words when aligned, one 32-bit word out)
-__global__ void __launch_bounds__(256) gray_kernel(const uint8_t *__restrict__ bgr, size_t n, int shift, uint8_t *__restrict__ out)
+__global__ void __launch_bounds__(256) gray_kernel(const uint8_t *__restrict__ bgr, size_t n, int shift, Expo ex, uint8_t *__restrict__ out)
 {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // group of 4 pixels
     const size_t p0 = q * 4;
@@ -32,18 +63,18 @@ __global__ void __launch_bounds__(256) gray_kernel(const uint8_t *__restrict__ b
         const uint32_t *w = reinterpret_cast<const uint32_t *>(bgr) + q * 3;
         const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
         // bytes: a = B0 G0 R0 B1 | b = G1 R1 B2 G2 | c = R2 B3 G3 R3
-        const unsigned g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255, shift);
-        const unsigned g1 = gray_of(a >> 24, b & 255, (b >> 8) & 255, shift);
-        const unsigned g2 = gray_of((b >> 16) & 255, b >> 24, c & 255, shift);
-        const unsigned g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24, shift);
+        const unsigned g0 = out_of(a & 255, (a >> 8) & 255, (a >> 16) & 255, shift, ex);
+        const unsigned g1 = out_of(a >> 24, b & 255, (b >> 8) & 255, shift, ex);
+        const unsigned g2 = out_of((b >> 16) & 255, b >> 24, c & 255, shift, ex);
+        const unsigned g3 = out_of((c >> 8) & 255, (c >> 16) & 255, c >> 24, shift, ex);
         reinterpret_cast<uint32_t *>(out)[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
         return;
     }
-    for (size_t p = p0; p < n && p < p0 + 4; p++) out[p] = (uint8_t)gray_of(bgr[3 * p], bgr[3 * p + 1], bgr[3 * p + 2], shift);
+    for (size_t p = p0; p < n && p < p0 + 4; p++) out[p] = (uint8_t)out_of(bgr[3 * p], bgr[3 * p + 1], bgr[3 * p + 2], shift, ex);
 }
 
 // factor f >= 2: one thread per output pixel, box sums of the three channels, OpenCV's rounding, then gray
-__global__ void __launch_bounds__(256) area_gray_kernel(const uint8_t *__restrict__ bgr, int sw, int W, int H, int f, int shift, uint8_t *__restrict__ out)
+__global__ void __launch_bounds__(256) area_gray_kernel(const uint8_t *__restrict__ bgr, int sw, int W, int H, int f, int shift, Expo ex, uint8_t *__restrict__ out)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -59,23 +90,26 @@ __global__ void __launch_bounds__(256) area_gray_kernel(const uint8_t *__restric
         b = (unsigned)__float2int_rn((float)s0 * scale); g = (unsigned)__float2int_rn((float)s1 * scale); r = (unsigned)__float2int_rn((float)s2 * scale);
         b = min(b, 255u); g = min(g, 255u); r = min(r, 255u);
     }
-    out[(size_t)y * W + x] = (uint8_t)gray_of(b, g, r, shift);
+    out[(size_t)y * W + x] = (uint8_t)out_of(b, g, r, shift, ex);
 }
 
 }  // namespace
 
-int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray)
+int k_ingest(mr_context *ctx, const uint8_t *d_bgr, int src_w, int src_h, uint8_t *d_gray, const float *exposure)
 {
+    Expo ex;
+    ex.on = exposure ? 1 : 0;
+    for (int c = 0; c < 3; c++) ex.e[c] = exposure ? exposure[c] : 0.f;
     const int W = ctx->W, H = ctx->H;
     if (src_w == W && src_h == H) {
         const size_t groups = (ctx->N + 3) / 4;
-        gray_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, ctx->stream>>>(d_bgr, ctx->N, ctx->gray_shift, d_gray);
+        gray_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, ctx->stream>>>(d_bgr, ctx->N, ctx->gray_shift, ex, d_gray);
         MR_LAUNCH_CHECK(ctx, "gray_kernel");
         return MR_OK;
     }
     const int f = src_w / W;
     dim3 b(32, 8), g(cdiv(W, 32), cdiv(H, 8));
-    area_gray_kernel<<<g, b, 0, ctx->stream>>>(d_bgr, src_w, W, H, f, ctx->gray_shift, d_gray);
+    area_gray_kernel<<<g, b, 0, ctx->stream>>>(d_bgr, src_w, W, H, f, ctx->gray_shift, ex, d_gray);
     MR_LAUNCH_CHECK(ctx, "area_gray_kernel");
     return MR_OK;
 }

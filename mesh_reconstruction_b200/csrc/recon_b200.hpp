@@ -201,12 +201,15 @@ inline void filterPoints(Mat &points, Mat &normals, float radius, int device = 0
 
 // == configuration.cpp:226-245 ==  what Configuration does to every decoded frame: cv::resize(INTER_AREA) to the render
 // size (integer factor) + cv::cvtColor(CV_BGR2GRAY)
-inline Mat ingestFrame(const Mat bgr, int width, int height, int device = 0)
+// exposure != nullptr: estimateExposure's three channel weights (B, G, R) of this frame replace the gray conversion
+// (configuration.cpp:417-425; the estimate itself is host work)
+inline Mat ingestFrame(const Mat bgr, int width, int height, int device = 0, const float *exposure = nullptr)
 {
     assert(bgr.channels() == 3 && bgr.depth == U8);
     mr_context *c = detail::ctx_for(width, height, device);
     Mat out(height, width, U8, 1);
-    detail::check(c, mr_ingest_frame(c, bgr.ptr<uint8_t>(), bgr.cols, bgr.rows, out.ptr<uint8_t>()));
+    if (exposure) detail::check(c, mr_ingest_frame_exposure(c, bgr.ptr<uint8_t>(), bgr.cols, bgr.rows, exposure, out.ptr<uint8_t>()));
+    else detail::check(c, mr_ingest_frame(c, bgr.ptr<uint8_t>(), bgr.cols, bgr.rows, out.ptr<uint8_t>()));
     return out;
 }
 

@@ -41,3 +41,32 @@ def test_ingest_argument_errors():
         mr.api.ingest_frame(ctx, np.zeros((72, 96, 3), np.uint8))      # factor 1.5
     with pytest.raises(mr.MeshReconError):
         ctx.check(ctx.lib.mr_set_gray_shift(ctx.h, 13))
+
+
+def _exposure_ref(bgr, e):
+    """configuration.cpp:417-425 with the OpenCV binary: frame = zeros; frame += channel[c] * exposure[c] (8-bit Mat
+    arithmetic: convertTo with a float scale, then a saturating add).  cv2.convertScaleAbs == convertTo for weights >= 0;
+    a negative weight saturates every product to 0."""
+    import cv2
+    ref = np.zeros(bgr.shape[:2], np.uint8)
+    for c in range(3):
+        t = cv2.convertScaleAbs(np.ascontiguousarray(bgr[..., c]), alpha=float(np.float32(e[c]))) if e[c] >= 0 else np.zeros_like(ref)
+        ref = cv2.add(ref, t)
+    return ref
+
+
+@pytest.mark.parametrize("W,H,f,e", [(640, 480, 1, (0.31, 0.36, 0.29)), (321, 243, 1, (0.5, 0.5, 0.5)), (640, 360, 2, (0.9, 0.7, 0.2)),
+                                     (160, 120, 3, (0.114, 0.587, 0.299)), (64, 48, 1, (1.7, -0.4, 0.3)), (64, 48, 1, (0.0, 0.0, 3.0e7))])
+def test_ingest_with_exposure_matches_cv2(W, H, f, e):
+    """Configuration::estimateExposure's frame normalisation (its estimate is host work; the per-pixel mix is the device part)."""
+    import cv2
+    rng = np.random.default_rng(W * 7 + f)
+    bgr = rng.integers(0, 256, (H * f, W * f, 3)).astype(np.uint8)
+    bgr[: H * f // 4] = rng.integers(0, 4, (H * f // 4, W * f, 3)) * 85
+    small = cv2.resize(bgr, (W, H), interpolation=cv2.INTER_AREA) if f > 1 else bgr
+    ref = _exposure_ref(small, e)
+    if e[2] > 1e6:        # 255 * 3e7 >= 2^31: cvRound gives the integer indefinite, which saturates to 0 (x86 cvtps2dq + packs)
+        ref = np.where(small[..., 2].astype(np.float32) * np.float32(e[2]) >= 2147483648.0, 0, ref).astype(np.uint8)
+    ctx = mr.api.Context(W, H)
+    got = mr.api.ingest_frame(ctx, bgr, exposure=e)
+    assert np.array_equal(got, ref), (np.abs(got.astype(int) - ref.astype(int)).max(), (got != ref).mean())
