@@ -202,34 +202,47 @@ __global__ void __launch_bounds__(128) fb_box_v_kernel(const float *__restrict__
         vs[(size_t)y * st + xc] = s;
     }
 }
-// horizontal part + 2x2 solve: one block per row segment, 2m+1 taps from shared memory
+// horizontal part + 2x2 solve: one block per row segment of FB_SEG * FB_RUN pixels staged in shared memory; every thread
+// owns FB_RUN consecutive pixels: 2m+1 taps for the first, then one add and one subtract per pixel (OpenCV's own
+// horizontal pass slides the same way; sums in double)
 #define FB_SEG 128
+#define FB_RUN 4
 __global__ void __launch_bounds__(FB_SEG) fb_box_h_solve_kernel(const double *__restrict__ vs, int W, int H, int m, int block_size,
                                                                 float *__restrict__ flow)
 {
-    extern __shared__ double seg[];   // (FB_SEG + 2m) * 5
-    const int y = blockIdx.y, x0 = blockIdx.x * FB_SEG;
+    extern __shared__ double seg[];   // (FB_SEG * FB_RUN + 2m) * 5
+    const int y = blockIdx.y, x0 = blockIdx.x * FB_SEG * FB_RUN;
     const double *row = vs + (size_t)y * W * 5;
-    const int n = (FB_SEG + 2 * m) * 5;
+    const int n = (FB_SEG * FB_RUN + 2 * m) * 5;
     for (int i = threadIdx.x; i < n; i += FB_SEG) {
         int xx = x0 - m + i / 5, c = i % 5;
         xx = min(max(xx, 0), W - 1);                                                         // replicated borders
         seg[i] = row[xx * 5 + c];
     }
     __syncthreads();
-    int x = x0 + threadIdx.x;
-    if (x >= W) return;
-    double g11 = 0, g12 = 0, g22 = 0, h1 = 0, h2 = 0;
-    const double *p = seg + threadIdx.x * 5;
+    const int xl = threadIdx.x * FB_RUN;                 // first pixel of the run, segment-local
+    if (x0 + xl >= W) return;
+    double g[5] = {0, 0, 0, 0, 0};
+    const double *p = seg + xl * 5;
     for (int t = 0; t <= 2 * m; t++) {
-        g11 += p[t * 5]; g12 += p[t * 5 + 1]; g22 += p[t * 5 + 2]; h1 += p[t * 5 + 3]; h2 += p[t * 5 + 4];
+#pragma unroll
+        for (int c = 0; c < 5; c++) g[c] += p[t * 5 + c];
     }
     const double scale = 1. / ((double)block_size * block_size);
-    double g11_ = g11 * scale, g12_ = g12 * scale, g22_ = g22 * scale, h1_ = h1 * scale, h2_ = h2 * scale;
-    double idet = 1. / (g11_ * g22_ - g12_ * g12_ + 1e-3);
-    size_t i = (size_t)y * W + x;
-    flow[i * 2] = (float)((g11_ * h2_ - g12_ * h1_) * idet);
-    flow[i * 2 + 1] = (float)((g22_ * h1_ - g12_ * h2_) * idet);
+#pragma unroll
+    for (int j = 0; j < FB_RUN; j++) {
+        const int x = x0 + xl + j;
+        if (x >= W) break;
+        if (j > 0) {
+#pragma unroll
+            for (int c = 0; c < 5; c++) g[c] += p[(j + 2 * m) * 5 + c] - p[(j - 1) * 5 + c];
+        }
+        double g11_ = g[0] * scale, g12_ = g[1] * scale, g22_ = g[2] * scale, h1_ = g[3] * scale, h2_ = g[4] * scale;
+        double idet = 1. / (g11_ * g22_ - g12_ * g12_ + 1e-3);
+        size_t i = (size_t)y * W + x;
+        flow[i * 2] = (float)((g11_ * h2_ - g12_ * h1_) * idet);
+        flow[i * 2 + 1] = (float)((g22_ * h1_ - g12_ * h2_) * idet);
+    }
 }
 
 __global__ void fb_pack_kernel(const float *__restrict__ flow2, size_t N, float4 *__restrict__ flow4)
@@ -371,7 +384,7 @@ int k_farneback(mr_context *ctx, const uint8_t *d_prev, const uint8_t *d_next, f
         for (int it = 0; it < iterations; it++) {
             fb_box_v_kernel<<<dim3(cdiv(w * 5, 128), cdiv(h, FB_VSEG)), 128, 0, ctx->stream>>>(M, w, h, m, vs);
             MR_LAUNCH_CHECK(ctx, "fb_box_v_kernel");
-            fb_box_h_solve_kernel<<<dim3(cdiv(w, FB_SEG), h), FB_SEG, (FB_SEG + 2 * m) * 5 * sizeof(double), ctx->stream>>>(vs, w, h, m, winsize, flow);
+            fb_box_h_solve_kernel<<<dim3(cdiv(w, FB_SEG * FB_RUN), h), FB_SEG, (FB_SEG * FB_RUN + 2 * m) * 5 * sizeof(double), ctx->stream>>>(vs, w, h, m, winsize, flow);
             MR_LAUNCH_CHECK(ctx, "fb_box_h_solve_kernel");
             if (it < iterations - 1) {
                 fb_update_matrices_kernel<<<g, b, 0, ctx->stream>>>(R0, R1, flow, w, h, M);
