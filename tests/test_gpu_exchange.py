@@ -55,6 +55,34 @@ for trial in range(3):
         assert int(x.slot(p, (1,), torch.int32, offset_bytes=SLOT_ROWS * 28)) == 1000 * trial + p
     dist.barrier()                                                       # nobody overwrites a slot a peer is still checking
 x.close()
+# the same exchange through an NVSwitch multicast mapping: ONE push per rank (multimem.st CTAs, then the copy-engine
+# variant) lands in every rank's buffer, the sender's own slot included
+if world > 1:
+    for mode in ("sm", "ce"):
+        os.environ["MR_MCAST_MODE"] = mode
+        try:
+            m = shard.McastExchange(ctx, SLOT_ROWS * 28 + 4, torch.device("cuda", local))
+        except RuntimeError as e:                                            # no NVSwitch multicast on this box: collective, every rank lands here
+            print("RANK", rank, "multicast unavailable:", e)
+            break
+        out = m.out((SLOT_ROWS, 7))
+        cnt = m.out((1,), torch.int32, offset_bytes=SLOT_ROWS * 28)
+        for trial in range(3):
+            src = torch.rand((SLOT_ROWS, 7), generator=g).cuda() + trial
+            with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream)):
+                out.copy_(src)
+                cnt.fill_(7000 * trial + rank)
+            m.push()
+            with torch.cuda.stream(m.signal_stream()):
+                dist.all_reduce(flag)
+            torch.cuda.synchronize()
+            ref, _ = shard.allgather_points(src, SLOT_ROWS)
+            for p in range(world):
+                assert torch.equal(m.slot(p, (SLOT_ROWS, 7)), ref[p * SLOT_ROWS:(p + 1) * SLOT_ROWS]), (mode, trial, p)
+                assert int(m.slot(p, (1,), torch.int32, offset_bytes=SLOT_ROWS * 28)) == 7000 * trial + p
+            dist.barrier()
+        m.close()
+        print("RANK", rank, "multicast", mode, "OK")
 # an output buffer that is too small on ANY rank is refused on EVERY rank (the abort is collective: nobody is left
 # waiting inside the row broadcasts), and so is a bad argument on one rank only
 import ctypes as C
