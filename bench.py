@@ -212,6 +212,9 @@ def main():
                          "slows the step is the 7 x 464 MB ARRIVING at every GPU, which multicast does not reduce)")
     ap.add_argument("--xchg-repeat", type=int, default=1,
                     help="debug: push every slot this many times (emulates the per-GPU exchange volume of a larger world on few GPUs)")
+    ap.add_argument("--xchg-from", type=int, default=-1,
+                    help="debug: only this rank pushes its slot (separates the cost of SENDING rows from that of RECEIVING them: "
+                         "compare diag.ms_by_rank); the content check is skipped")
     ap.add_argument("--graphs", type=int, default=None, choices=[0, 1, 2],
                     help="mr_set_use_graphs mode (default: the library's: graph replay when rows go to the host or with --farneback)")
     ap.add_argument("--farneback", action="store_true", help="run the reference's -f branch (not the headline configuration)")
@@ -361,7 +364,8 @@ def main():
                 # into every peer's buffer over NVLink, stream-ordered after this step's kernels; a 4-byte all-reduce entered
                 # after the pushes is the completion signal (when it is done everywhere, every slot of set k has landed)
                 for _ in range(max(1, args.xchg_repeat)):
-                    xch[k].push()
+                    if args.xchg_from < 0 or args.xchg_from == rank:
+                        xch[k].push()
                 with torch.cuda.stream(xch[k].signal_stream()):
                     pending[k] = (dist.all_reduce(xflag[k], async_op=True),)
             else:
@@ -546,7 +550,7 @@ def main():
             r_.ctx.synchronize()
         torch.cuda.synchronize()
         dist.barrier()
-        if use_p2p:
+        if use_p2p and args.xchg_from < 0:
             from mesh_reconstruction_b200 import shard
             bad = 0
             for k_ in range(nbuf):
