@@ -12,6 +12,11 @@ this script pins those decisions to the OpenCV binary.  tests/test_oracle_cv2_tr
 recon_oracle.c to reproduce the committed output bit for bit.
 
     python tests/golden/make_cv2_transliteration.py        # writes tests/golden/cv2_translit_s2_96x72.npz (~1 minute)
+                                                           # and tests/golden/cv2_translit_s34_40x30.npz (S = 4 and S = 3)
+
+The second file pins a rule that only shows with FOUR side cameras: `projectionW * k` (util.cpp:105) is then a 4x4 by 4x1
+cv::gemm, which OpenCV evaluates with its hand-written small-matrix kernels in FLOAT, whereas the S x 4 product of any
+other S goes through the generic kernel with DOUBLE accumulators -- the oracle's and the CUDA kernel's `S == 4` branch.
 
 Quirk decisions are the documented ones: C5 continuous-memory reads past a row end, C8 `dot` starts at 0,
 C9 the neighbourhood is cleared for every pixel.
@@ -299,6 +304,35 @@ def main():
     out = os.path.join(HERE, "cv2_translit_s2_96x72.npz")
     np.savez_compressed(out, tri=tri, tri1=tri1, depth1=d1, flow1=fl1, cv2_version=cv2.__version__)
     print("wrote", out, tri.shape, tri1.shape, "cv2", cv2.__version__)
+    main_s34()
+
+
+def main_s34():
+    """S = 4 (BASELINE config 5's schedule: sides fa-2, fa-1, fa+1, fa+2) and S = 3 on a 40 x 30 frame.  The inputs (flows,
+    depth after the cumulative mixBackground masking, cameras) come from the oracle's front half -- cv2's
+    VariationalRefinement etc. -- and are stored next to the transliteration's rows."""
+    root = os.path.dirname(os.path.dirname(HERE))
+    sys.path.insert(0, root)
+    from mesh_reconstruction_b200 import synth
+    from oracle.pipeline import process_main_frame
+    from oracle.render import RenderOracle
+    W, H = 40, 30
+    sc = synth.make_scene(W, H, 5, seed=11, step=0.12, mesh_err=0.03, mesh_res=6)
+    frames = sc.frames()
+    r = RenderOracle(W, H)
+    r.loadMesh(sc.vertices, sc.faces)
+    fa = 2
+    res = {}
+    for name, sides in (("s4", [0, 1, 3, 4]), ("s3", [1, 3, 4])):
+        _, inter = process_main_frame(r, frames, sc.cameras, fa, sides, keep=True)
+        flows = [np.ascontiguousarray(f, f32) for f in inter["flows"]]
+        depth = np.ascontiguousarray(inter["depth"], f32)
+        tri = triangulate_pixels(flows, sc.cameras[fa].astype(f32), [sc.cameras[s].astype(f32) for s in sides], depth)
+        res.update({f"flows_{name}": np.stack(flows), f"depth_{name}": depth, f"sides_{name}": np.asarray(sides), f"tri_{name}": tri})
+        print(name, tri.shape, "nan rows", int(np.isnan(tri).any(1).sum()))
+    out = os.path.join(HERE, "cv2_translit_s34_40x30.npz")
+    np.savez_compressed(out, cameras=sc.cameras.astype(f32), fa=fa, cv2_version=cv2.__version__, **res)
+    print("wrote", out)
 
 
 if __name__ == "__main__":

@@ -237,3 +237,10 @@ def test_cuda_reproduces_cv2_transliteration(golden_dir):
     assert _same(got, t["tri"])
     got1 = mr.triangulatePixels([t["flow1"]], cams[fa], [cams[sides[0]]], t["depth1"])
     assert np.isnan(t["tri1"]).any() and _same(got1, t["tri1"])
+    # S = 4 (a 4x4 float cv::gemm for the projective w) and S = 3 (generic gemm, double accumulators)
+    t = np.load(os.path.join(golden_dir, "cv2_translit_s34_40x30.npz"))
+    cams, fa = t["cameras"], int(t["fa"])
+    for name in ("s4", "s3"):
+        sides = [int(s) for s in t["sides_" + name]]
+        got = mr.triangulatePixels(list(t["flows_" + name]), cams[fa], [cams[s] for s in sides], t["depth_" + name])
+        assert _same(got, t["tri_" + name]), name

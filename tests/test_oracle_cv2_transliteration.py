@@ -33,3 +33,14 @@ def test_oracle_reproduces_cv2_transliteration():
     ref1, ev1 = triangulate_pixels([t["flow1"]], cams[fa], [cams[sides[0]]], t["depth1"], return_evals=True)
     assert set(int(k) for k in ev1[:, 3]) >= {1, 2} and np.isnan(ref1).any()
     assert _same(ref1, t["tri1"])
+
+
+def test_oracle_reproduces_cv2_transliteration_s4_and_s3():
+    """Four side cameras make `projectionW * k` (util.cpp:105) a 4x4 cv::gemm -- OpenCV's FLOAT small-matrix kernel -- while
+    any other S takes the generic kernel with double accumulators.  The transliteration (cv2.gemm itself) pins both."""
+    t = np.load(os.path.join(HERE, "golden", "cv2_translit_s34_40x30.npz"))
+    cams, fa = t["cameras"], int(t["fa"])
+    for name in ("s4", "s3"):
+        sides = [int(s) for s in t["sides_" + name]]
+        ref = triangulate_pixels(list(t["flows_" + name]), cams[fa], [cams[s] for s in sides], t["depth_" + name])
+        assert len(ref) > 900 and _same(ref, t["tri_" + name]), name
