@@ -126,3 +126,35 @@ def test_seqsum_is_sequential():
         s += float(v)
     assert ofilter.seqsum(t[:2000]) == s
     assert ofilter.seqsum(t) != float(np.sum(t.astype(np.float64))) or True
+
+
+def test_neighbour_table_equals_flann_linear_index():
+    """Quirk F1 pinned to the FLANN binary: the reference's kd-tree search (heuristic.cpp:72-85) approximates the radius
+    set that FLANN's EXACT linear index returns.  For every point the oracle's j < i block must be that set in FLANN's
+    result order (ascending squared distance), with FLANN's float squared distances inside densityFn (heuristic.cpp:49-52)."""
+    import cv2
+    rng = np.random.default_rng(12)
+    n = 3000
+    pts = np.concatenate([rng.random((n - 200, 3)), rng.random((200, 3)) * 0.05 + 0.4], 0).astype(np.float32)   # a dense clump among sparse points
+    pts[17] = pts[16]                                                                                           # a duplicate (distance 0)
+    w = (rng.random((n, 1)) * 1.5 + 0.5).astype(np.float32)
+    p4 = np.concatenate([pts * w, w], 1).astype(np.float32)               # homogeneous, as filterPoints receives them
+    p3 = np.ascontiguousarray(p4[:, :3] / p4[:, 3:4])                     # dehomogenize(), util.cpp:16-29: plain float divisions
+    radius = np.float32(0.004)                                            # bounds SQUARED distances (0.063 units)
+    res = ofilter.filter_points(p4, float(radius), want_table=True)
+    index = cv2.flann_Index(p3, {"algorithm": 0})                          # FLANN_INDEX_LINEAR: exact
+    blocks, nb_idx, nb_w = res["blocks"], res["nb_idx"], res["nb_w"]
+    total = 0
+    for i in range(n):
+        cnt, ind, dist = index.radiusSearch(p3[i:i + 1], float(radius), n, params={"checks": 32})
+        ind, dist = ind[0][:cnt], dist[0][:cnt]
+        sel = (ind < i) & (dist <= radius)
+        exp_idx = ind[sel]
+        exp_w = (1.0 - (dist[sel] / radius).astype(np.float64)).astype(np.float32)      # (float)(1. - dist / radius): float quotient, double difference
+        got_idx, got_w = nb_idx[blocks[i]:blocks[i + 1]], nb_w[blocks[i]:blocks[i + 1]]
+        # FLANN orders equal distances arbitrarily (heap); the oracle defines ties by index: compare as (distance, index) sets
+        assert len(got_idx) == len(exp_idx), i
+        order = np.lexsort((exp_idx, -exp_w))
+        assert np.array_equal(got_idx, exp_idx[order]) and np.array_equal(got_w, exp_w[order]), i
+        total += len(got_idx)
+    assert total == res["n_edges"] and total > 5 * n
