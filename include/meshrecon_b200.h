@@ -187,8 +187,10 @@ int mr_xchg_push_mcast(mr_context *ctx, void *mcast_dst, const void *src, size_t
 /* ---- frame ingest  configuration.cpp:226-245 -------------------------------------------------------
  * What Configuration does to every decoded frame before the path sees it: cv::resize(frame, Size(width, height),
  * CV_INTER_AREA) when the clip is larger than the render size (the -s scaling factor), then cv::cvtColor(CV_BGR2GRAY).
- * bgr: src_height x src_width x 3 uint8 (host -- ideally a pinned ring buffer the decoder writes into -- or device);
- * the frame must be the context's size times ONE integer factor (the reference warns about anything else);
+ * bgr: src_height x src_width x 3 uint8 (host -- ideally a pinned ring buffer the decoder writes into -- or device), at
+ * least the context's size in both directions: integer factors take OpenCV's fast area path (integer box sums), anything
+ * else (`-s 1.5`: the reference only warns when the size is not divisible, configuration.cpp:149-151) its general one
+ * (float cell weights);
  * out_gray: H x W uint8, host or device (pass the device frame buffer mr_process_main_frame will read).  Arithmetic is
  * OpenCV's (integer box sums + its rounding, fixed-point gray), bit-identical to the cv2 binary.  Video decoding and
  * estimateExposure (off by default, configuration.cpp:25) stay on the host.  Asynchronous for device outputs

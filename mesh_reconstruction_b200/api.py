@@ -451,7 +451,7 @@ def filter_info(ctx, want_arrays=False, n=None):
 
 def ingest_frame(ctx, bgr, out=None, exposure=None):
     """``mr_ingest_frame``: what configuration.cpp:226-245 does to a decoded frame -- ``cv::resize(INTER_AREA)`` to the
-    context's size when the frame is an integer multiple of it, then ``cv::cvtColor(BGR2GRAY)``.  ``bgr``: h x w x 3 uint8
+    context's size when the frame is larger (integer or fractional factors, OpenCV's fast / general area paths), then ``cv::cvtColor(BGR2GRAY)``.  ``bgr``: h x w x 3 uint8
     (NumPy / pinned or CUDA tensor); returns the H x W gray frame (NumPy, or ``out`` -- e.g. a CUDA tensor)."""
     h, w = int(bgr.shape[0]), int(bgr.shape[1])
     pb, kb = _ptr(bgr, np.uint8)

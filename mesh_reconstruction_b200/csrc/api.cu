@@ -831,9 +831,8 @@ static int ingest_impl(mr_context *ctx, const uint8_t *bgr, int src_width, int s
     CHECK_CTX(ctx);
     SET_DEVICE(ctx);
     CHECK_ARG(ctx, bgr && out_gray, "null argument");
-    CHECK_ARG(ctx, src_width >= ctx->W && src_height >= ctx->H && src_width % ctx->W == 0 && src_height % ctx->H == 0 &&
-                       src_width / ctx->W == src_height / ctx->H,
-              "the frame must be the render size times one integer factor in both directions (configuration.cpp:149-151)");
+    CHECK_ARG(ctx, src_width >= ctx->W && src_height >= ctx->H && src_width <= 64 * ctx->W && src_height <= 64 * ctx->H,
+              "the frame must be at least the render size in both directions (INTER_AREA shrinks, configuration.cpp:232-233)");
     const size_t in_bytes = (size_t)src_width * src_height * 3;
     const uint8_t *d_in = (const uint8_t *)mr_in(ctx, bgr, in_bytes, "in_bgr");
     const bool dev_out = mr_is_device_ptr(out_gray);

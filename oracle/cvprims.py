@@ -434,3 +434,56 @@ def gemm_f32(a, b):
                 c[i, j] = s
         return c
     return (a.astype(np.float64) @ b.astype(np.float64)).astype(f32)
+
+
+# ---------------------------------------------------------------------------
+# cv::resize(..., INTER_AREA) on CV_8UC<cn> for a NON-integer shrink factor (configuration.cpp:232-233 with a fractional
+# -s): OpenCV's computeResizeAreaTab + ResizeArea_Invoker<uchar, float>, restated; bit-exact vs cv2 (tests/test_oracle_cv.py).
+# (Integer factors take resizeAreaFast_ instead; the CUDA ingest follows the same split.)
+# ---------------------------------------------------------------------------
+def _area_tab(ssize, dsize):
+    import math
+    scale = float(ssize) / dsize
+    tab = []
+    for d in range(dsize):
+        fs1 = d * scale
+        fs2 = fs1 + scale
+        cell = min(scale, ssize - fs1)
+        s1, s2 = math.ceil(fs1), math.floor(fs2)
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        if s1 - fs1 > 1e-3:
+            tab.append((d, s1 - 1, f32((s1 - fs1) / cell)))
+        for sx in range(s1, s2):
+            tab.append((d, sx, f32(1.0 / cell)))
+        if fs2 - s2 > 1e-3:
+            tab.append((d, s2, f32(min(min(fs2 - s2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_8u(src, W, H):
+    """``cv2.resize(src, (W, H), interpolation=cv2.INTER_AREA)`` for uint8 ``src`` (h x w or h x w x cn) being SHRUNK by a
+    factor that is not an integer in both directions."""
+    sh, sw = src.shape[:2]
+    cn = src.shape[2] if src.ndim == 3 else 1
+    s = src.reshape(sh, sw, cn)
+    xtab, ytab = _area_tab(sw, W), _area_tab(sh, H)
+    xd = np.array([t[0] for t in xtab])
+    xs = np.array([t[1] for t in xtab])
+    xa = np.array([t[2] for t in xtab], f32)
+    dst = np.zeros((H, W, cn), np.uint8)
+    acc = np.zeros((W, cn), f32)
+    prev = ytab[0][0]
+    for dy, sy, beta in ytab:
+        buf = np.zeros((W, cn), f32)
+        row = s[sy].astype(f32)
+        for k in range(len(xtab)):                       # float accumulation in table order
+            buf[xd[k]] = buf[xd[k]] + row[xs[k]] * xa[k]
+        if dy != prev:
+            dst[prev] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+            acc = beta * buf
+            prev = dy
+        else:
+            acc = acc + beta * buf
+    dst[prev] = np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+    return dst if src.ndim == 3 else dst[..., 0]

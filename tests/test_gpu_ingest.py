@@ -34,13 +34,30 @@ def test_ingest_matches_cv2(W, H, f):
 
 def test_ingest_argument_errors():
     ctx = mr.api.Context(64, 48)
-    bad = np.zeros((48 * 2, 64 * 3, 3), np.uint8)          # different factors in x and y
     with pytest.raises(mr.MeshReconError):
-        mr.api.ingest_frame(ctx, bad)
+        mr.api.ingest_frame(ctx, np.zeros((40, 64, 3), np.uint8))      # smaller than the render size: INTER_AREA only shrinks here
     with pytest.raises(mr.MeshReconError):
-        mr.api.ingest_frame(ctx, np.zeros((72, 96, 3), np.uint8))      # factor 1.5
+        mr.api.ingest_frame(ctx, np.zeros((48, 63, 3), np.uint8))
     with pytest.raises(mr.MeshReconError):
         ctx.check(ctx.lib.mr_set_gray_shift(ctx.h, 13))
+
+
+@pytest.mark.parametrize("sw,sh,W,H", [(960, 540, 640, 360), (1000, 700, 400, 280), (97, 61, 33, 20), (1920, 1080, 1280, 720), (50, 50, 49, 49),
+                                       (120, 54, 48, 36), (64, 90, 64, 36), (192, 144, 64, 72), (64, 96, 64, 48), (3840, 2160, 1536, 864)])
+def test_ingest_fractional_and_mixed_factors_match_cv2(sw, sh, W, H):
+    """`-s 1.5`, `-s 2.5` ... (configuration.cpp:160-163): cv::resize's GENERAL area path (float cell weights), and integer
+    factors that differ in x and y (OpenCV's fast path with fx != fy): byte-exact against the cv2 binary, gray and exposure mix."""
+    import cv2
+    rng = np.random.default_rng(sw * 3 + H)
+    bgr = rng.integers(0, 256, (sh, sw, 3)).astype(np.uint8)
+    bgr[: sh // 3] = rng.integers(0, 4, (sh // 3, sw, 3)) * 85
+    small = cv2.resize(bgr, (W, H), interpolation=cv2.INTER_AREA)
+    ctx = mr.api.Context(W, H)
+    got = mr.api.ingest_frame(ctx, bgr)
+    ref = cv2.cvtColor(small, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(got, ref), (np.abs(got.astype(int) - ref.astype(int)).max(), (got != ref).mean())
+    e = (0.4, 0.35, 0.3)
+    assert np.array_equal(mr.api.ingest_frame(ctx, bgr, exposure=e), _exposure_ref(small, e))
 
 
 def _exposure_ref(bgr, e):

@@ -167,3 +167,13 @@ def test_farneback_restatement_matches_cv2():
     mine = fb.farneback(p, n)
     assert np.abs(ref - mine).max() < 1e-4
     assert abs(np.median(ref[..., 0]) - 1.3) < 0.1 and abs(np.median(ref[..., 1]) + 0.7) < 0.1
+
+
+@pytest.mark.parametrize("sw,sh,W,H", [(96, 72, 64, 48), (100, 70, 40, 28), (97, 61, 33, 20), (50, 50, 49, 49), (120, 54, 48, 36), (64, 90, 64, 36)])
+def test_general_inter_area_restatement_bit_exact(sw, sh, W, H):
+    """cv::resize INTER_AREA for the fractional shrink factors a `-s 1.5` run produces (configuration.cpp:160-163, 232-233)."""
+    rng = np.random.default_rng(sw + W)
+    src = rng.integers(0, 256, (sh, sw, 3)).astype(np.uint8)
+    src[: sh // 3] = rng.integers(0, 2, (sh // 3, sw, 3)) * 255
+    assert np.array_equal(P.resize_area_8u(src, W, H), cv2.resize(src, (W, H), interpolation=cv2.INTER_AREA))
+    assert np.array_equal(P.resize_area_8u(src[..., 0], W, H), cv2.resize(np.ascontiguousarray(src[..., 0]), (W, H), interpolation=cv2.INTER_AREA))
