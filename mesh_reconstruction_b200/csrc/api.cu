@@ -309,8 +309,15 @@ int mr_depth_samples(mr_context *ctx, const float *cameras, int n_cameras, const
         if (!d_cams) return mr_fail(ctx, MR_ENOMEM, "mr_depth_samples", "alloc");
         RC(k_depth_query(ctx, d_cams, n_cameras, d_rows, d_cols, n_per_camera, d_out));
     } else {
+        std::vector<float> h_cams;                 // the raster launches take the matrix by value: it has to be readable here
+        const float *cams_host = cameras;
+        if (mr_is_device_ptr(cameras)) {
+            h_cams.resize((size_t)n_cameras * 16);
+            MR_CUDA(ctx, cudaMemcpy(h_cams.data(), cameras, h_cams.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            cams_host = h_cams.data();
+        }
         for (int i = 0; i < n_cameras; i++) {      // many queries per viewer: render each map, index it on the device
-            RC(k_raster(ctx, to_mat4(cameras + 16 * i), vis));
+            RC(k_raster(ctx, to_mat4(cams_host + 16 * i), vis));
             RC(k_depth_samples(ctx, vis, d_rows + (size_t)i * n_per_camera, d_cols + (size_t)i * n_per_camera, n_per_camera,
                                d_out + (size_t)i * n_per_camera));
         }
