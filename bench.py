@@ -212,6 +212,8 @@ def main():
                          "slows the step is the 7 x 464 MB ARRIVING at every GPU, which multicast does not reduce)")
     ap.add_argument("--xchg-repeat", type=int, default=1,
                     help="debug: push every slot this many times (emulates the per-GPU exchange volume of a larger world on few GPUs)")
+    ap.add_argument("--no-e2e-balance", action="store_true",
+                    help="N > 1: give every rank the same number of main frames per e2e step even when their host links differ")
     ap.add_argument("--xchg-from", type=int, default=-1,
                     help="debug: only this rank pushes its slot (separates the cost of SENDING rows from that of RECEIVING them: "
                          "compare diag.ms_by_rank); the content check is skipped")
@@ -324,9 +326,11 @@ def main():
         rows_dev = [torch.empty((B, N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)]   # normals kernel writes straight into the send buffer
         counts_dev = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(nbuf)]
     # every pair of a step lands on the host; two alternating sets so that the host reads step s-1 while step s runs
-    rows_pin = [[torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(B)] for _ in range(2)]
-    counts_pin = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)]
-    per_ctx = [len(range(c, B, nctx)) for c in range(nctx)]     # pairs each context gets per step
+    # (N > 1: a rank behind a faster host link takes up to 1.5 B main frames per e2e step, see balance_e2e below)
+    Bmax = B if world == 1 or args.no_e2e_balance else B + (B + 1) // 2
+    rows_pin = [[torch.empty((N, 7), dtype=torch.float32).pin_memory() for _ in range(Bmax)] for _ in range(2)]
+    counts_pin = [torch.zeros(Bmax, dtype=torch.int32).pin_memory() for _ in range(2)]
+    e2e_B = {"mine": B, "all": [B] * world}                     # main frames per e2e step of this rank / of every rank
     counts = torch.zeros(B, dtype=torch.int64)
     rows_flat = [r.view(B * N, 7) for r in rows_dev]
     gather_rows = [torch.empty((world * B * N, 7), dtype=torch.float32, device=dev) for _ in range(nbuf)] if world > 1 and not use_p2p else None
@@ -382,12 +386,13 @@ def main():
         # result of step s-1 has landed (mr_wait_copies_until: all but this step's copies) and reads it -- a two-deep
         # pipeline of pinned buffer sets, the way a long-running reconstruction consumes its main frames.
         k = s & 1
-        for b in range(B):
-            a, cs = pair(s * B + b)
+        Be = e2e_B["mine"]
+        for b in range(Be):
+            a, cs = pair(s * Be + b)
             mr.submit_main_frame(renders[b % nctx], frames_pin[a], cams[idx[a]], [frames_pin[c] for c in cs], [cams[idx[c]] for c in cs],
                                  out=rows_pin[k][b], out_count=counts_pin[k][b:b + 1])
         for c_, r_ in enumerate(renders):
-            r_.ctx.wait_copies_until(per_ctx[c_])
+            r_.ctx.wait_copies_until(len(range(c_, Be, nctx)))       # all but this step's copies of that context
         return int(counts_pin[k ^ 1].sum())
 
     def drain_e2e():
@@ -431,6 +436,58 @@ def main():
             ms = float(allt[:, 0].max())
         return ms, sum(r_.ctx.launches for r_ in renders) - l0
 
+    # ---- host link: every rank copies device -> pinned host at once for ~0.3 s (outside the timed regions) ----------------
+    def probe_link():
+        for r_ in renders:
+            r_.ctx.synchronize()
+        src_rows = rows_dev[0].view(-1)[: N * 7 * min(B, 4)]
+        dst_rows = [rows_pin[0][b].view(-1) for b in range(min(B, 4))]
+        chunk = N * 7
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+        def burst(reps):
+            for i in range(reps):
+                with torch.cuda.stream(streams[i & 1]):
+                    j = i % len(dst_rows)
+                    dst_rows[j].copy_(src_rows[j * chunk:(j + 1) * chunk], non_blocking=True)
+        burst(4)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(8, int(args.link_probe_s * 50e9 / (chunk * 4)))
+        e0.record(torch.cuda.current_stream())
+        for st_ in streams:
+            st_.wait_stream(torch.cuda.current_stream())
+        burst(reps)
+        for st_ in streams:
+            torch.cuda.current_stream().wait_stream(st_)
+        e1.record(torch.cuda.current_stream())
+        barrier()
+        ms_probe = e0.elapsed_time(e1)
+        mine_gbs = reps * chunk * 4 / (ms_probe * 1e-3) / 1e9
+        if world > 1:
+            t = torch.tensor([ms_probe, mine_gbs], dtype=torch.float64, device=dev)
+            allp = torch.empty((world, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allp, t)
+            # equal_split_gbs: what the ranks deliver together when each has the same bytes to move (the slowest link sets the
+            # time); sum_gbs: when each moves bytes in proportion to its own rate
+            return {"equal_split_gbs": world * reps * chunk * 4 / (float(allp[:, 0].max()) * 1e-3) / 1e9,
+                    "sum_gbs": float(allp[:, 1].sum()), "by_rank_gbs": [round(float(v), 1) for v in allp[:, 1]]}
+        return {"equal_split_gbs": mine_gbs, "sum_gbs": mine_gbs, "by_rank_gbs": [round(mine_gbs, 1)]}
+
+    def balance_e2e(link, ms_frame_compute):
+        """e2e at N > 1 is bound by the host links, and on this pool's boxes they are not equal (four GPUs reach ~12 GB/s, four
+        ~18 GB/s when all copy at once).  Main frames are independent, so every rank takes them in proportion to the rate it
+        can sustain: one frame costs it max(compute time, row bytes / its link rate)."""
+        if world == 1 or args.no_e2e_balance or not link:
+            return
+        rates = link["by_rank_gbs"]
+        if min(rates) <= 0:
+            return
+        ms_frame_link = [(N * 28 + 4) / (r_ * 1e9) * 1e3 for r_ in rates]
+        w = [1.0 / max(ms_frame_compute, t_) for t_ in ms_frame_link]
+        e2e_B["all"] = [min(Bmax, max(1, int(round(B * world * w_ / sum(w))))) for w_ in w]
+        e2e_B["mine"] = e2e_B["all"][rank]
+
     # ---- warm-up, then the timed regions ---------------------------------------------------
     for s in range(Wm):
         step_resident(s)
@@ -439,6 +496,8 @@ def main():
     ms_res, launches = timed(step_resident, K, Wm)
     diag_res = dict(diag)
     sampler.stop_flag = True
+    link = probe_link() if args.link_probe_s > 0 else None
+    balance_e2e(link, ms_res / K / B)
     for s in range(max(Wm - 2, 1)):
         step_e2e(s)
     drain_e2e()
@@ -501,45 +560,8 @@ def main():
                            "iterations, 441-term sequential window sums): every large kernel is issue- or XU/FP64-pipe bound, DRAM throughput is 1-3 %"}
     pix_total = world * B * K * N * S
     value = pix_total / (ms_res * 1e-3) / 1e6
-    e2e_val = pix_total / (ms_e2e * 1e-3) / 1e6
+    e2e_val = sum(e2e_B["all"]) * K * N * S / (ms_e2e * 1e-3) / 1e6
     m_mean = float(counts_dev[(Wm + K - 1) % nbuf].float().mean())
-
-    # ---- host link ceiling: every rank copies device -> pinned host at once for ~0.3 s (outside the timed regions) --------
-    link = None
-    if args.link_probe_s > 0:
-        for r_ in renders:
-            r_.ctx.synchronize()
-        src_rows = rows_dev[0].view(-1)[: N * 7 * min(B, 4)]
-        dst_rows = [rows_pin[0][b].view(-1) for b in range(min(B, 4))]
-        chunk = N * 7
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-
-        def burst(reps):
-            for i in range(reps):
-                with torch.cuda.stream(streams[i & 1]):
-                    j = i % len(dst_rows)
-                    dst_rows[j].copy_(src_rows[j * chunk:(j + 1) * chunk], non_blocking=True)
-        burst(4)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(8, int(args.link_probe_s * 50e9 / (chunk * 4)))
-        e0.record(torch.cuda.current_stream())
-        for st_ in streams:
-            st_.wait_stream(torch.cuda.current_stream())
-        burst(reps)
-        for st_ in streams:
-            torch.cuda.current_stream().wait_stream(st_)
-        e1.record(torch.cuda.current_stream())
-        barrier()
-        ms_probe = e0.elapsed_time(e1)
-        mine_gbs = reps * chunk * 4 / (ms_probe * 1e-3) / 1e9
-        if world > 1:
-            t = torch.tensor([ms_probe, mine_gbs], dtype=torch.float64, device=dev)
-            allp = torch.empty((world, 2), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(allp, t)
-            link = {"aggregate_gbs": world * reps * chunk * 4 / (float(allp[:, 0].max()) * 1e-3) / 1e9, "by_rank_gbs": [round(float(v), 1) for v in allp[:, 1]]}
-        else:
-            link = {"aggregate_gbs": mine_gbs, "by_rank_gbs": [round(mine_gbs, 1)]}
 
     # ---- exchange content check (N > 1, outside the timed regions): every slot every rank received equals, bit for bit,
     # what its producer holds; and the compacted rank-ordered cloud (the reference's append order, recon.cpp:115-116)
@@ -626,15 +648,21 @@ def main():
             filt = {"error": str(e)[:200]}
 
     if rank == 0:
-        d2h_step = (N * 28 + 4) * B
-        e2e = {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": (1 + S) * N * B, "d2h_bytes_per_step": d2h_step,   # the DMA moves the full row capacity (count unknown on the host without a sync)
-               "rows_bytes_per_step": int(m_mean * 28 * B), "ms_per_step": ms_e2e / K}
+        fr_step = sum(e2e_B["all"]) / world                      # main frames per step and GPU (mean over ranks)
+        d2h_step = (N * 28 + 4) * fr_step
+        e2e = {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": int((1 + S) * N * fr_step), "d2h_bytes_per_step": int(d2h_step),   # per GPU; the DMA moves the full row capacity (count unknown on the host without a sync)
+               "rows_bytes_per_step": int(m_mean * 28 * fr_step), "ms_per_step": ms_e2e / K}
+        if world > 1:
+            e2e["main_frames_per_step_by_rank"] = e2e_B["all"]
         if link:
-            # share of the probed host-link ceiling (all ranks copying at once) that the e2e run's row traffic reaches
-            e2e["host_link_gbs"] = link["aggregate_gbs"]
+            # share of the probed host-link capacity that the e2e run's row traffic reaches.  host_link_gbs: every rank copying the
+            # SAME number of bytes at once (the slowest link sets the time); the sum of the per-rank rates is an upper bound that
+            # sustained traffic does not reach (measured: 97 of 122 GB/s with frames divided in proportion to the rates)
+            e2e["host_link_gbs"] = link["equal_split_gbs"]
+            e2e["host_link_sum_of_rank_rates_gbs"] = link["sum_gbs"]
             e2e["host_link_by_rank_gbs"] = link["by_rank_gbs"]
             e2e["d2h_achieved_gbs"] = world * d2h_step / (ms_e2e / K * 1e-3) / 1e9
-            e2e["host_link_frac"] = e2e["d2h_achieved_gbs"] / link["aggregate_gbs"]
+            e2e["host_link_frac"] = e2e["d2h_achieved_gbs"] / link["equal_split_gbs"]
             e2e["bound"] = "host link" if e2e["host_link_frac"] > 0.85 else "compute"
         line = {
             "metric": "Mpix/s matched+triangulated", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
