@@ -47,3 +47,19 @@ fr = sc.frames()
 r = mr.Render(W, H, ctx=mr.api.Context(W, H)); r.loadMesh(verts, sc.faces)
 tri = mr.process_main_frame(r, fr[1], cams[1], [fr[0], fr[2]], [cams[0], cams[2]])
 print("translated", tri.shape, r.ctx.normals_stats())
+
+# round 2, second half: the rasteriser's work split (small boxes / lists + persistent warps / row spans, a viewer INSIDE the mesh,
+# the direct grid of small meshes), the ray-query depth shots, the general INTER_AREA ingest and the exposure mix
+from tests.test_gpu_parity_r2 import face_camera
+W, H = 200, 150
+for res in (6, 48):                                   # 72 faces: direct grid; 4608 faces: lists
+    sc = synth.make_scene(W, H, 2, mesh_res=res, mesh_err=0.05, amp=0.3)
+    r = mr.Render(W, H, ctx=mr.api.Context(W, H)); r.loadMesh(sc.vertices, sc.faces)
+    P = face_camera(sc.vertices, sc.faces, len(sc.faces) // 2, 10.0, 0.5, 0.3, 0.4)
+    d_out, d_in = r.depth(sc.cameras[0]), r.depth(P)
+    q = r.depthSamples(np.stack([sc.cameras[0], P]), np.tile(np.arange(0, 150, 10, dtype=np.int32), (2, 1)), np.tile(np.arange(0, 195, 13, dtype=np.int32), (2, 1)))
+    big = r.depthSamples(sc.cameras[:1], np.random.default_rng(1).integers(0, H, (1, 5000)).astype(np.int32), np.random.default_rng(2).integers(0, W, (1, 5000)).astype(np.int32))
+    print("raster", len(sc.faces), float((d_out != 1).mean()), float((d_in != 1).mean()), q.shape, big.shape)
+bgr = np.random.default_rng(3).integers(0, 256, (108, 192, 3)).astype(np.uint8)
+c = mr.api.Context(128, 72)
+print("ingest 1.5x", int(mr.api.ingest_frame(c, bgr).sum()), int(mr.api.ingest_frame(c, bgr, exposure=(0.4, 0.3, 0.3)).sum()))
