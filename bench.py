@@ -140,8 +140,8 @@ def cpu_reference_pairs(scene, frames, pairs, threads, farneback=False):
 def workload_name(args):
     W, H, S = args.width, args.height, args.sides
     if args.config == 5:
-        return f"synthetic {W}x{H} {args.frames}-frame sequence, multi-baseline matching (S={S}: sides i-2, i-1, i+1, i+2) + triangulation (BASELINE config 5)"
-    return f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S={S} (BASELINE config 4)"
+        return f"synthetic {W}x{H} {args.frames}-frame sequence, multi-baseline matching (S={S}: sides i-2, i-1, i+1, i+2) + triangulation (BASELINE config 5); surface height z0 = {args.scene_z0:g}"
+    return f"synthetic {W}x{H} {args.frames}-frame sequence, adjacent-pair matching + triangulation, S={S} (BASELINE config 4); surface height z0 = {args.scene_z0:g}"
 
 
 def run_reference(args):
@@ -156,7 +156,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     S = args.sides
     nfr = 4 + 2 * (S // 2) if S > 1 else 4
-    scene = synth.make_scene(W, H, nfr, step=args.cam_step, mesh_err=args.mesh_err)
+    scene = synth.make_scene(W, H, nfr, step=args.cam_step, mesh_err=args.mesh_err, z0=args.scene_z0)
     frames = {i: scene.frame(i) for i in range(nfr)}
     lo, hi = main_range(nfr, S)
     pairs_cycle = [(a, sides_of(a, S)) for a in range(lo, hi)]
@@ -199,6 +199,11 @@ def main():
     ap.add_argument("--no-filter-bench", action="store_true", help="skip the filterPoints measurement (N = 1, after the timed regions)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this rank (and its pinned host buffers) to the CPUs local to its GPU")
     ap.add_argument("--link-probe-s", type=float, default=0.3, help="seconds of the all-ranks D2H probe that measures the host link ceiling (0 = skip)")
+    ap.add_argument("--scene-z0", type=float, default=-2.7,
+                    help="world height z0 of the synthetic surface z = z0 + a sin(fx x) sin(fy y) (SURVEY 8(d)).  Default: the world origin sits "
+                         "at the camera path, like in the reference's own tracks (tracks/*.yaml: bundle depths -3.9 .. -2.3, x and y around 0); "
+                         "0 puts the surface ON the z = 0 plane -- the worst case of the bit-exact window-PCA kernel (every window near a zero "
+                         "of z is accumulated sample by sample), the setting of rounds 1 and 2 up to profiles/bench_r2_final_*")
     ap.add_argument("--cam-step", type=float, default=0.006)
     ap.add_argument("--mesh-err", type=float, default=0.02)
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame pairs timed for cpu_baseline (rank 0, N=1)")
@@ -255,7 +260,7 @@ def main():
         lib.mr_set_vr_impl(args.vr_impl)
 
     # ---- synthetic sequence: this rank's contiguous block of main frames --------------------
-    scene = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err)
+    scene = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err, z0=args.scene_z0)
     block = max(2, args.frames // world)
     start = rank * block
     n_local = min(block, B * (K + Wm) + 1 + 2 * (S // 2), args.frames - start)
@@ -604,7 +609,7 @@ def main():
         cores = os.cpu_count() or 1
         n_main = max(1, args.cpu_pairs // S)
         fr = {i: frames_pin[i].numpy() for i in range(min(n_local, n_main + 2 * (S // 2) + (1 if S == 1 else 0)))}
-        sc4 = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err)
+        sc4 = synth.make_scene(W, H, args.frames, step=args.cam_step, mesh_err=args.mesh_err, z0=args.scene_z0)
         sc4.cameras = cams[idx[0]:idx[0] + len(fr)]
         lo_, hi_ = main_range(len(fr), S)
         prs = [(a_, sides_of(a_, S)) for a_ in range(lo_, hi_)][:n_main]
@@ -625,7 +630,10 @@ def main():
             fin = torch.isfinite(rows0).all(1)
             rows0 = rows0[fin].contiguous()
             d3 = rows0[:, :3] / rows0[:, 3:4]
-            spacing = float((d3[:, 0].max() - d3[:, 0].min())) / W
+            # pixel spacing on the surface from the 1 % .. 99 % range of x: a handful of rows are far outliers (pixels whose
+            # Newton iteration ran away -- reference behaviour), and a radius derived from the raw extent would be absurd
+            qs = torch.quantile(d3[::8, 0].contiguous(), torch.tensor([0.01, 0.99], device=dev))
+            spacing = float(qs[1] - qs[0]) / (0.98 * W)
             radius = (3.0 * spacing) ** 2
             out_rows = torch.empty_like(rows0)
             mr.filter_rows(rows0, radius, ctx=ctx, out=out_rows)          # first call allocates the tables

@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <climits>
 #include <cmath>
@@ -610,6 +611,10 @@ int k_seqsum(mr_context *ctx, const float *d_terms, long long n, double *h_out)
     return MR_OK;
 }
 
+struct IntToI64 {
+    __host__ __device__ long long operator()(int v) const { return (long long)v; }
+};
+
 #define CUB_CALL(ctx, expr)                                                         \
     do {                                                                            \
         size_t bytes__ = 0;                                                         \
@@ -661,8 +666,11 @@ int k_filter_points(mr_context *ctx, const float *d_pts, int pstride, const floa
     }
     tm.lap("cells + neighbour count");
     MR_CUDA(ctx, cudaMemsetAsync(off, 0, 2 * ((size_t)n + 1) * sizeof(long long), st));
-    CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntL, offL + 1, n, st));
-    CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntU, offU + 1, n, st));
+    // the counts are scanned as 64-bit values: CUB accumulates in the INPUT type, and a radius that is too large for the cloud
+    // (more than 2^31 pairs) must come out as a number that the check below can refuse, not as a wrapped int
+    cub::TransformInputIterator<long long, IntToI64, const int *> cntL64(cntL, IntToI64()), cntU64(cntU, IntToI64());
+    CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntL64, offL + 1, n, st));
+    CUB_CALL(ctx, cub::DeviceScan::InclusiveSum(tmp__, bytes__, cntU64, offU + 1, n, st));
     long long hE[2] = {0, 0};
     MR_CUDA(ctx, cudaMemcpyAsync(&hE[0], offL + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaMemcpyAsync(&hE[1], offU + n, sizeof(long long), cudaMemcpyDeviceToHost, st));

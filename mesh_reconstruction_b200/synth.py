@@ -127,7 +127,7 @@ class Scene:
 
 
 def make_scene(width, height, n_frames, seed=0, step=0.01, mesh_res=24, mesh_err=0.004,
-               extent=1.6, amp=0.05, dist=3.0, fov=0.92, tex_components=24):
+               extent=1.6, amp=0.05, dist=3.0, fov=0.92, tex_components=24, z0=0.0):
     """Build the synthetic sequence of BASELINE config 4/5 at any size.
 
     The camera travels on an arc above the surface, ``step`` world units per
@@ -161,6 +161,12 @@ def make_scene(width, height, n_frames, seed=0, step=0.01, mesh_res=24, mesh_err
         c = look_at(eye, (0.15 * s, 0.0, 0.0))
         c2w.append(c)
         cams.append((persp @ np.linalg.inv(c)).astype(f32))
+    if z0 != 0.0:
+        T = np.eye(4)
+        T[2, 3] = z0                                        # world = T . scene
+        Ti = np.linalg.inv(T)
+        verts = (verts.astype(np.float64) @ T.T).astype(f32)
+        cams = [(persp @ np.linalg.inv(c) @ Ti).astype(f32) for c in c2w]
     lo, hi = verts[:, :3].min(0), verts[:, :3].max(0)
     return Scene(width, height, np.stack(cams), np.stack(c2w), verts, faces, amp, fxs, fys, tex,
                  fov, near, far, float(np.linalg.norm(hi - lo)))

@@ -127,15 +127,15 @@ def _pixel_of_rows(rows, P, W, H):
     return row, col
 
 
-@pytest.mark.parametrize("W,H,S,with_oracle", [(1920, 1080, 1, True), (3840, 2160, 4, True)])
-def test_full_size_properties(W, H, S, with_oracle):
+@pytest.mark.parametrize("W,H,S,with_oracle,z0", [(1920, 1080, 1, True, 0.0), (1920, 1080, 1, True, -2.7), (3840, 2160, 4, True, 0.0), (3840, 2160, 1, True, -2.7)])
+def test_full_size_properties(W, H, S, with_oracle, z0):
     """BASELINE configs 4 (1080p, S=1) and 5 (4K, S=4) at full size.  Properties: determinism; the fused
     call equals the sequence of individual entry points bit for bit; rows come out in row-major pixel
     order, one per surviving pixel; and the full oracle comparison at both sizes (the 4K, S = 4 oracle run takes ~10-30 s of
     host time): every flow of every side camera and every point row bit for bit."""
     n = S + 1
-    sc = synth.make_scene(W, H, 300, step=0.006, mesh_err=0.02)
-    fa = 150
+    sc = synth.make_scene(W, H, 300, step=0.006, mesh_err=0.02, z0=z0)     # z0 = 0: surface on the z = 0 plane (sample loops of the
+    fa = 150                                                                # normals kernel); -2.7: bench.py's default (integer route)
     sides = ([fa + 1] if S == 1 else [fa - 2, fa - 1, fa + 1, fa + 2])
     frames = {i: sc.frame(i) for i in [fa] + sides}
     r = mr.Render(W, H, ctx=mr.api.Context(W, H))

@@ -130,3 +130,20 @@ def test_filter_rows_of_the_path():
     got_rows_h, keep_h = mr.filter_rows(rows, radius, ctx=r.ctx)          # host buffers through the same entry point
     assert np.array_equal(keep_h, ref["keep"]) and np.array_equal(got_rows_h, rows[ref["keep"]])
     assert 0 < len(ref["keep"]) < len(rows)
+
+
+def test_too_many_pairs_is_refused_not_wrapped():
+    """More than 2^31 neighbour pairs (a radius far too large for the cloud; the reference's own `int` table would overflow):
+    the call must fail with MR_EINVAL -- the pair counts are scanned in 64 bits, so the total cannot wrap to a small or negative
+    number and be used to size the tables."""
+    rng = np.random.default_rng(5)
+    n = 70000                                                   # n^2 / 2 = 2.45e9 pairs when every point sees every other
+    p = np.concatenate([rng.random((n, 3)).astype(np.float32) * 0.01, np.ones((n, 1), np.float32)], 1)
+    ctx = mr.api.Context(16, 16)
+    with pytest.raises(mr.MeshReconError) as e:
+        mr.filterPoints(p, np.zeros((n, 3), np.float32), 1.0, ctx=ctx)
+    assert "2^31" in str(e.value)
+    # the context stays usable
+    q = p[:2000]
+    _, _, keep = mr.filterPoints(q, np.zeros((len(q), 3), np.float32), 1e-6, ctx=ctx)
+    assert len(keep) > 0
