@@ -50,25 +50,38 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons (NVML, every few ms) while the timed region runs."""
+    """Samples SM clocks / throttle reasons (NVML, every few ms) while the timed region runs.  NVML is initialised in the
+    constructor and the thread is started BEFORE the warm-up (a cold nvmlInit can take longer than a short timed region);
+    samples are only kept while `recording` is set."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], 0, None
-
-    def run(self):
+        self.index, self.stop_flag, self.recording, self.sm, self.reasons, self.max_sm = index, False, False, [], 0, None
+        self.nv = self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            self.reasons |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
             while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    self.reasons |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                time.sleep(0.004)
+                if self.recording:
+                    self.sample()
+                time.sleep(0.003)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
 
@@ -412,7 +425,7 @@ def main():
 
     diag = dict(diag0)
 
-    def timed(fn, steps, first, drain=None):
+    def timed(fn, steps, first, drain=None, sampler=None):
         for k in range(nbuf):
             wait_pending(k)
         barrier()
@@ -423,6 +436,11 @@ def main():
         for s in range(steps):
             fn(first + s)
         diag["host_ms_per_step"] = (time.perf_counter() - t_host) * 1e3 / steps     # CPU time to queue a step
+        if sampler is not None and sampler.nv is not None:
+            try:
+                sampler.sample()          # the queue is still draining here: at least one sample under load, whatever the thread's timing
+            except Exception:  # noqa: BLE001
+                pass
         if drain is not None:
             drain()
         if world > 1:
@@ -494,11 +512,13 @@ def main():
         e2e_B["mine"] = e2e_B["all"][rank]
 
     # ---- warm-up, then the timed regions ---------------------------------------------------
-    for s in range(Wm):
-        step_resident(s)
     sampler = ClockSampler(local)
     sampler.start()
-    ms_res, launches = timed(step_resident, K, Wm)
+    for s in range(Wm):
+        step_resident(s)
+    sampler.recording = True
+    ms_res, launches = timed(step_resident, K, Wm, sampler=sampler)
+    sampler.recording = False
     diag_res = dict(diag)
     sampler.stop_flag = True
     link = probe_link() if args.link_probe_s > 0 else None
