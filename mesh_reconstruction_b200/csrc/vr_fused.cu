@@ -10,15 +10,17 @@
 //   region D (tile + 10)   : Ix, Iy, Iz, du, dv, w -> shared memory, red/black SPLIT layout: each colour of
 //                                                     the checkerboard is a dense array, so every neighbour
 //                                                     access of a warp is unit-stride (no bank conflicts)
-//   region C (tile +  9)   : A11, A12, A22, b1, b2 -> REGISTERS of the owning thread (7 column pairs each)
+//   region C (tile +  9)   : A11, A12, A22, b1, b2 -> REGISTERS of the owning thread (6 column pairs each)
 //
 // Dependency radius of one iteration is 10 (one pixel per SOR half-sweep), +1 for the weights, +2 for
 // the derivatives; halo pixels keep being updated with stale neighbours after their values stop
 // mattering, and that contamination travels inwards one pixel per half-sweep, i.e. it never reaches
 // the tile.  Arithmetic and operation order are those of vr_math.cuh (bit-exact vs cv2), -fmad=false.
 //
-// Thread layout: 42 x 12.  Thread (tx, ty) owns column pair tx (D-local columns 2tx, 2tx+1) of rows
-// 1 + ty + 12k, k = 0..6; the row parity -- hence which column of the pair is red -- is fixed per
+// Thread layout: 42 x 14 (588 of the 608 threads; 6 rows each keep the kernel at 96 registers, i.e. 58K of the SM's 64K:
+// the 7K left are one 128-thread CTA of the Newton kernel of another context -- with 42 x 12 / 7 rows / 128 registers the VR CTA
+// owned the whole register file).  Thread (tx, ty) owns column pair tx (D-local columns 2tx, 2tx+1) of rows
+// 1 + ty + 14k, k = 0..5; the row parity -- hence which column of the pair is red -- is fixed per
 // thread, and every shared-memory address is `base + k * const`.
 #include <cstddef>
 #include <cuda.h>
@@ -35,10 +37,10 @@ constexpr int DW = OTW + 2 * HALO, DH = OTH + 2 * HALO;    // region D (origin =
 constexpr int NP = DW / 2;                                 // column pairs per row == entries per colour per row
 constexpr int IX_OFF = 16, IY_OFF = HALO + 1;              // image tile origin = tile - (16, 11): x must be 16-byte aligned for TMA
 constexpr int IPITCH = 96, IH = DH + 2;                    // image tile: 96 bytes x 86 rows
-constexpr int TY = 12;                                     // thread rows
-constexpr int NT = 512;                                    // threads per CTA (NP * TY = 504 active in the pair phases)
-constexpr int SLOTS = (DH - 2 + TY - 1) / TY;              // rows owned per thread in the pair phases (7)
-constexpr int RSLOTS = DH / TY;                            // rows owned per thread in the staging phases (7)
+constexpr int TY = 14;                                     // thread rows
+constexpr int NT = 608;                                    // threads per CTA (NP * TY = 588 active in the pair phases)
+constexpr int SLOTS = (DH - 2 + TY - 1) / TY;              // rows owned per thread in the pair phases (6)
+constexpr int RSLOTS = DH / TY;                            // rows owned per thread in the staging phases (6)
 constexpr int PLANE = DH * NP;                             // floats per colour per plane
 static_assert(DW % 2 == 0 && NP * TY <= NT && (TY % 2) == 0 && (HALO % 2) == 0 && (OTW % 2) == 0, "thread layout");
 static_assert(IX_OFF + OTW + HALO + 1 <= IPITCH, "image tile width");
@@ -59,8 +61,8 @@ static_assert(offsetof(Smem, Iy) == offsetof(Smem, Ix) + sizeof(float) * 2 * PLA
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // du / dv of region D from the previous iteration (zero on the first one and outside the image), then the first
-// derivatives and the smoothness weights on D.  Same 42 x 12 layout as the pair phases: thread (tx, ty) owns
-// column pair tx of rows ty + 12k, k = 0..6 (DH == 7 * 12), so the colour of the pair's first column is ty & 1
+// derivatives and the smoothness weights on D.  Same 42 x 14 layout as the pair phases: thread (tx, ty) owns
+// column pair tx of rows ty + 14k, k = 0..5 (DH == 6 * 14), so the colour of the pair's first column is ty & 1
 // for every slot and all 14 global loads of a thread are in flight together.
 template <bool INTERIOR, bool FIRST, bool USE_TMA>
 __device__ __forceinline__ void stage_phases(Smem &s, const int tid, const int dx0, const int dy0, const int ix0, const int iy0,
