@@ -249,7 +249,8 @@ def triangulate_pixels(flows, mainCamera, cameras, depth):                      
                 continue
             pdf = points[pid, 4]
             if S > 1:
-                pdf = f32(math.pow(float(pdf), 1.0 / S))
+                with np.errstate(all="ignore"):
+                    pdf = f32(np.power(np.float64(pdf), np.float64(1.0 / S)))        # C pow(): NaN for a negative base, no exception
             nb = []
             for ny in range(row - radius, row + radius + 1):
                 if ny < 0 or ny >= H:

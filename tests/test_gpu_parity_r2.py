@@ -244,3 +244,30 @@ def test_cuda_reproduces_cv2_transliteration(golden_dir):
         sides = [int(s) for s in t["sides_" + name]]
         got = mr.triangulatePixels(list(t["flows_" + name]), cams[fa], [cams[s] for s in sides], t["depth_" + name])
         assert _same(got, t["tri_" + name]), name
+
+
+def test_random_small_cases_match_oracle():
+    """The random cases on which tests/test_oracle_cv2_transliteration.py pins the oracle to a LIVE cv2-level transliteration
+    (holes in the depth map, zero variances, negative pdf -> NaN through pow, S = 1, 2, 4, 5, both scene origins): the CUDA
+    rows must equal the oracle's bit for bit."""
+    from oracle.render import RenderOracle
+    from oracle.tri import triangulate_pixels
+    W, H = 14, 10
+    for seed, S in [(0, 1), (1, 2), (2, 4), (3, 5), (4, 4)]:
+        rng = np.random.default_rng(100 + seed)
+        sc = synth.make_scene(W, H, S + 1, seed=seed, step=0.1, mesh_res=4, z0=(-2.7 if seed % 2 else 0.0))
+        ro = RenderOracle(W, H)
+        ro.loadMesh(sc.vertices, sc.faces)
+        depth = ro.depth(sc.cameras[0]).copy()
+        depth[rng.random((H, W)) < 0.15] = 1.0
+        flows = []
+        for _ in range(S):
+            f = np.zeros((H, W, 4), np.float32)
+            f[..., :2] = rng.normal(0, 0.4, (H, W, 2))
+            f[..., 2] = rng.uniform(0.05, 3.0, (H, W))
+            f[..., 2][rng.random((H, W)) < 0.03] = 0.0
+            flows.append(f)
+        cams = [sc.cameras[i].astype(np.float32) for i in range(S + 1)]
+        ref = triangulate_pixels(flows, cams[0], cams[1:], depth)
+        got = mr.triangulatePixels(flows, cams[0], cams[1:], depth)
+        assert _same(got, ref), (seed, S, got.shape, ref.shape)
